@@ -1,0 +1,199 @@
+"""Pin the oracle (oracle/pyref.py, oracle/dcarl_oracle.c) against outputs of the
+reference itself (tests/golden/*.npz, written by tools/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import cport, pyref
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def _state_major(idx, x, S):
+    return np.concatenate([x[idx == s] for s in range(S)])
+
+
+def test_c_sum_is_numpy_sum_bit_exact():
+    rng = np.random.default_rng(0)
+    for n in list(range(1, 300)) + [511, 512, 513, 1000, 1917, 4097, 20000]:
+        x = rng.normal(3, 50, n)
+        assert cport.np_sum(x) == float(np.sum(x)), n
+
+
+def test_bounds_golden(golden):
+    g = golden("bounds")
+    off = np.concatenate([[0], np.cumsum(g["lens"])])
+    for i in range(len(g["lens"]) - 1):
+        x = g["flat"][off[i]:off[i + 1]]
+        want = g["out"][i]
+        got_py = [pyref.upper_bound(x), pyref.lower_bound(x), pyref.CI_lower_bound(x), pyref.mean_value(x)]
+        assert np.array_equal(np.asarray(got_py, np.float64), want)
+        assert np.array_equal(np.asarray(cport.bounds(x)), want), i
+    x = g["flat"][off[-2]:]
+    alpha, _, scale = g["last_kwargs"]
+    assert np.array_equal(np.asarray(cport.bounds(x, alpha=alpha, scale=scale)), g["out"][-1])
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_stream_golden_c_port(golden, which):
+    g = golden(f"sim{which}")
+    S, A, N = int(g["S"]), int(g["A"]), int(g["n_rows"])
+    idx, act, R = g["idx"][:N].astype(np.int32), g["act"][:N].astype(np.int32), g["R"][:N]
+    out = cport.stream(idx, act, R, S, A)
+    assert np.array_equal(out["act"], g["step_act"])
+    assert np.array_equal(out["value"], g["step_value"])          # bit-exact float64
+    assert np.array_equal(out["activation_step"], g["activation_step"])
+    assert _sha(_state_major(idx, out["act"].astype(np.int64), S)) == str(g["sha_act_state_major"])
+    assert _sha(_state_major(idx, out["value"], S)) == str(g["sha_val_state_major"])
+    if "overall_value" in g.files:
+        assert np.array_equal(out["overall"], g["overall_value"])
+    # true_step_TSRL_value is a gather of the chosen action (ST1:96)
+    tav = g["true_action_values"]
+    assert np.array_equal(tav[idx, out["act"]], g["true_step_value"])
+
+
+def test_stream_golden_survey_facts(golden):
+    """The known answers SURVEY.md section 8(c) lists."""
+    g1, g2 = golden("sim1"), golden("sim2")
+    assert g1["activation_step"].tolist() == [4438]
+    assert str(g1["sha_act_state_major"]) == "f5edd4dd18133905"
+    assert str(g1["sha_val_state_major"]) == "6427704d17fa50e0"
+    assert g1["step_value"][1999] == 59.65865955874082 and g1["step_act"][19999] == 1
+    assert g2["activation_step"].tolist() == [-1, -1, 163, -1, -1, -1, 126, 196, 671, 729, 929,
+                                              796, 94, -1, -1, -1, -1, -1, -1, -1]
+    assert g2["overall_value"][-1] == 597.7193818873668
+    assert str(g2["sha_act_state_major"]) == "16a7aa31bc133fc0"
+
+
+def test_stream_golden_python_literal(golden):
+    """The slow literal restatement on Sim 2 (Sim 1 is quadratic: first 6000 rows only)."""
+    g = golden("sim2")
+    N = int(g["n_rows"])
+    data = np.stack([g["idx"][:N], g["state"][:N], g["act"][:N], g["R"][:N]], axis=1).astype(np.float64)
+    out = pyref.stream(data, int(g["S"]), int(g["A"]))
+    assert np.array_equal(out["act"], g["step_act"])
+    assert np.array_equal(out["value"], g["step_value"])
+    assert np.array_equal(out["overall"], g["overall_value"])
+    assert np.array_equal(out["activation_step"], g["activation_step"])
+    assert np.array_equal(out["final_value"], g["final_value"])
+    g = golden("sim1")
+    n = 6000
+    data = np.stack([g["idx"][:n], g["state"][:n], g["act"][:n], g["R"][:n]], axis=1).astype(np.float64)
+    out = pyref.stream(data, 1, 30, want_overall=False)
+    assert np.array_equal(out["value"], g["step_value"][:n])
+    assert np.array_equal(out["act"], g["step_act"][:n])
+
+
+def test_stream_incremental_variant_close(golden):
+    """Running-sum algebra (what the GPU uses): same argmax on the shipped data, values ~1e-11."""
+    for which in (1, 2):
+        g = golden(f"sim{which}")
+        N = int(g["n_rows"])
+        out = cport.stream(g["idx"][:N], g["act"][:N], g["R"][:N], int(g["S"]), int(g["A"]), incremental=True)
+        assert np.array_equal(out["act"], g["step_act"])
+        assert np.abs(out["value"] - g["step_value"]).max() < 1e-9
+        assert np.array_equal(out["activation_step"], g["activation_step"])
+
+
+def test_stream_edge_cases():
+    p = cport.default_params()
+    # empty stream
+    out = cport.stream(np.zeros((1, 0), np.int32), np.zeros((1, 0), np.int32), np.zeros((1, 0)), 3, 4, p)
+    assert out["activation_step"].tolist() == [[-1, -1, -1]]
+    # exactly n_thres samples never updates; the (n_thres+1)-th does (strict >, ST1:86)
+    idx = np.zeros(11, np.int32)
+    act = np.ones(11, np.int32)
+    R = np.full(11, 500.0)
+    out = cport.stream(idx, act, R, 1, 3, p)
+    assert out["value"][:10].tolist() == [100.0] * 10 and out["act"][:10].tolist() == [0] * 10
+    assert out["act"][10] == 1 and out["activation_step"].tolist() == [11]
+    # out-of-range key is an error
+    with pytest.raises(ValueError):
+        cport.stream(np.array([5], np.int32), np.array([0], np.int32), np.array([0.0]), 3, 4, p)
+    # python-literal and C agree on a random small case with ties and a non-zero rule action
+    rng = np.random.default_rng(5)
+    N, S, A = 3000, 3, 5
+    idx = rng.integers(0, S, N).astype(np.int32)
+    act = rng.integers(0, A, N).astype(np.int32)
+    R = np.round(rng.normal(40, 60, N))
+    data = np.stack([idx, np.zeros(N), act, R], 1).astype(np.float64)
+    a = pyref.stream(data, S, A, rule_act=2, n_thres=4)
+    b = cport.stream(idx, act, R, S, A, cport.default_params(rule_act=2, n_thres=4))
+    for k in ("value", "act", "overall", "activation_step"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_box_golden(golden):
+    g = golden("rls_box")
+    vs, vv, dr, dist = g["visited_state"], g["visited_value"], g["driving_record"], g["dist"]
+    assert dr.shape == (107, 29) and np.all(dr[:, 20] == 0)
+    nmv = cport.box_moments(vs, vv[:, 1], dist, dr[:, :20], 8)
+    assert np.array_equal(nmv[:, 0, 0], dr[:, 23])                       # visited times: exact
+    assert np.abs(nmv[:, 0, 1] - dr[:, 24]).max() < 1e-6                 # logged with %f
+    assert np.abs(nmv[:, 0, 2] - dr[:, 25]).max() < 1e-6
+    assert np.array_equal(nmv[:, 0, :], g["exact_nmv"])                  # float64 exact vs numpy on the full buffer
+    # python-literal buffer agrees with the C port on every candidate action and the pick
+    buf = pyref.BoxBuffer(vs, vv)
+    picks = cport.box_select(nmv)
+    for qi in range(0, 107, 9):
+        obs = dr[qi, :20]
+        for a in range(8):
+            q = np.append(obs, a)
+            n = buf.calculate_visited_times(q)
+            m, v, _ = buf.calculate_statistics_index(q)
+            assert (n, m, v) == tuple(nmv[qi, a])
+        assert int(buf.act_test(obs)) == picks[qi]
+
+
+def test_box_select_candidate_branch():
+    """act_test's a>=1 branch is not exercised by any reference artefact: pin C vs the literal port."""
+    rng = np.random.default_rng(11)
+    D = 20
+    dist = pyref.VISITED_STATE_DIST[0]
+    centers = rng.normal(0, 1, (6, D)) * dist[:D]
+    rows, vals = [], []
+    for c in centers:
+        for a in range(8):
+            m = int(rng.integers(0, 40))
+            s = c + rng.uniform(-0.45, 0.45, (m, D)) * dist[:D]
+            rows.append(np.hstack([s, np.full((m, 1), float(a))]))
+            r = -0.95 ** rng.integers(0, 10, m) * (rng.random(m) < (0.3 + 0.08 * a))
+            vals.append(np.stack([np.full(m, float(a)), r], 1))
+    vs, vv = np.vstack(rows), np.vstack(vals)
+    buf = pyref.BoxBuffer(vs, vv)
+    nmv = cport.box_moments(vs, vv[:, 1], dist, centers, 8)
+    picks = cport.box_select(nmv)
+    assert picks.max() > 0 and picks.min() == 0
+    for qi, c in enumerate(centers):
+        assert int(buf.act_test(c)) == picks[qi]
+
+
+def test_sampling_golden(golden):
+    g = golden("sampling")
+    data, av, st = pyref.data_generation(g["u_states"], g["u_action_values"], g["z_state"], g["act"], g["z_ret"])
+    assert np.array_equal(data, g["data"]) and np.array_equal(av, g["action_value"]) and np.array_equal(st, g["states"])
+    # C port: per-draw layout (rejected draws keep idx=-1)
+    z = g["z_state"]
+    idx_all = np.floor((3 + z) / 6 * 20).astype(int)
+    valid = (idx_all >= 0) & (idx_all < 20)
+    act_full = np.zeros(len(z), np.int32)
+    zr_full = np.zeros(len(z))
+    act_full[valid] = g["act"]
+    zr_full[valid] = g["z_ret"]
+    idx, R, nv = cport.sample_returns(g["action_value"], z, act_full, zr_full)
+    assert nv == len(g["data"]) == valid.sum()
+    assert np.array_equal(idx[valid], g["data"][:, 0]) and np.all(idx[~valid] == -1)
+    assert np.array_equal(R[valid], g["data"][:, 3])
+
+
+def test_add_data_returns():
+    """RLS:185-215: lagged rewards, then terminal reward discounted back."""
+    rew = [0.0] * 14 + [-1.0]
+    done = [False] * 14 + [True]
+    out = pyref.add_data_returns(rew, done)
+    assert [t for t, _ in out] == list(range(15))
+    assert [r for _, r in out[:5]] == [0.0] * 5                       # popped with their own reward
+    assert out[-1][1] == -1.0 and out[-2][1] == -0.95 and out[5][1] == -1.0 * 0.95 ** 9
