@@ -1,0 +1,111 @@
+"""ctypes binding of libdcarl_b200.so (include/dcarl_b200.h).  No torch types cross the
+boundary: tensors are passed as ``data_ptr()`` integers, the stream as a raw handle.
+
+The library is the only compute path of this package.  If it is missing, or no CUDA
+device is present, every compute call raises — there is no CPU fallback.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "lib", "libdcarl_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "dcarl_b200.h")
+_lib = None
+
+
+class DcarlError(RuntimeError):
+    """A C-ABI call returned non-zero (code < 0: bad argument index, > 0: cudaError_t)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"dcarl_b200: {msg} (code {code})")
+        self.code = code
+
+
+class Params(C.Structure):
+    """dcarl_params — constants of test_DCARL.py:10-12, 43-52."""
+    _fields_ = [("alpha", C.c_double), ("scale", C.c_double), ("cap", C.c_double),
+                ("prior_rule", C.c_double), ("prior_other", C.c_double),
+                ("activation_bonus", C.c_double), ("n_thres", C.c_int32), ("rule_act", C.c_int32)]
+
+    def __init__(self, alpha=0.05, scale=150.0, cap=100.0, prior_rule=100.0, prior_other=-50.0,
+                 activation_bonus=0.9, n_thres=10, rule_act=0):
+        super().__init__(alpha, scale, cap, prior_rule, prior_other, activation_bonus, n_thres, rule_act)
+
+
+class RlsParams(C.Structure):
+    """dcarl_rls_params — constants of RLS.act_test (RLS.py:120-157)."""
+    _fields_ = [("rule_mean_gate", C.c_double), ("confidence_thres", C.c_double),
+                ("visited_times_thres", C.c_int32), ("min_candidate_visits", C.c_int32)]
+
+    def __init__(self, rule_mean_gate=-0.1, confidence_thres=0.5, visited_times_thres=10,
+                 min_candidate_visits=5):
+        super().__init__(rule_mean_gate, confidence_thres, visited_times_thres, min_candidate_visits)
+
+
+_vp, _i32, _i64, _sz, _d, _f, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_double, C.c_float, C.c_uint64
+_int = C.c_int
+
+# name -> (restype, argtypes); must list every symbol include/dcarl_b200.h declares
+SIGNATURES = {
+    "dcarl_last_error": (C.c_char_p, []),
+    "dcarl_abi_version": (_int, []),
+    "dcarl_device_info": (_int, [C.POINTER(_int)] * 3),
+    "dcarl_default_params": (None, [C.POINTER(Params)]),
+    "dcarl_default_rls_params": (None, [C.POINTER(RlsParams)]),
+    "dcarl_bounds": (_int, [_vp, _int, _vp, _i64, C.POINTER(Params), _vp, _vp]),
+    "dcarl_stream_bounds_ws": (_sz, [_i64, _i64, _i32, _i32]),
+    "dcarl_stream_bounds": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i32, _i32, C.POINTER(Params),
+                                   _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
+    "dcarl_stream_stats": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "dcarl_sample_returns": (_int, [_vp, _int, _vp, _vp, _int, _vp, _i64, _i32, _i32, _d, _d, _d, _d,
+                                    _vp, _vp, _int, _vp]),
+    "dcarl_sample_returns_philox": (_int, [_vp, _int, _u64, _i64, _i32, _i32, _d, _d, _d, _d,
+                                           _vp, _vp, _vp, _int, _vp]),
+    "dcarl_box_moments_ws": (_sz, [_i32, _i32, _i32]),
+    "dcarl_box_moments": (_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "dcarl_box_select": (_int, [_vp, _i32, _i32, C.POINTER(RlsParams), _vp, _vp, _vp]),
+    "dcarl_rollout_cv": (_int, [_vp, _vp, _i64, _i32, _f, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
+}
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into lib/libdcarl_b200.so (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_DIR, "csrc"), "-j8"], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    """Load the shared library (once).  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"dcarl_b200: CUDA library not built ({LIB_PATH} missing). Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C dcarl_b200/csrc`. "
+                "There is no CPU fallback.")
+        try:
+            import torch  # noqa: F401  (loads the CUDA runtime the library shares)
+        except Exception:
+            pass
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.dcarl_abi_version() != 1:
+            raise RuntimeError("dcarl_b200: ABI version mismatch between _abi.py and the built library")
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise DcarlError(code, lib().dcarl_last_error().decode())
+
+
+def device_info():
+    sm, mj, mn = _int(), _int(), _int()
+    check(lib().dcarl_device_info(C.byref(sm), C.byref(mj), C.byref(mn)))
+    return sm.value, mj.value, mn.value

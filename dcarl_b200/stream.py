@@ -1,0 +1,188 @@
+"""Streaming confidence-bound estimator + argmax selector on the GPU.
+
+Drop-in for the ``__main__`` loops of Simulation_testing/Simulation_1/test_DCARL.py:73-99 and
+Simulation_testing/Simulation_2/test_DCARL.py:72-105, batched over independent scenario
+instances.  Array in, array out: numpy in -> numpy out (host<->device copies inside),
+CUDA tensors in -> CUDA tensors out (no copies, asynchronous on the current stream).
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _abi, _dev
+
+STATS_HEADER = 5   # DCARL_STATS_HEADER
+
+
+@dataclass
+class StreamResult:
+    value: object            # [n_inst, n_steps] max_a value[idx][a] per row        (step_TSRL_value)
+    act: object              # [n_inst, n_steps] int32 argmax per row              (step_TSRL_act)
+    activation_step: object  # [n_inst, S] int64, -1 = never                        (activation_step)
+    overall: Optional[object]  # [n_inst, n_steps] or None                          (overall_value)
+    act_hist: Optional[object] = None   # [A] uint64 histogram of act (int64 tensor)
+    stats: Optional[object] = None      # [5 + A] float64 summary vector (see dcarl_stream_stats)
+
+
+class StreamPlan:
+    """Pre-allocated device (and pinned host) buffers for repeated batches of one shape."""
+
+    def __init__(self, n_inst, n_steps, S, A, params=None, *, r_dtype=torch.float32,
+                 out_dtype=torch.float32, want_overall=True, want_stats=True, variant=0, device=None):
+        _dev.require_cuda()
+        self.n_inst, self.n_steps, self.S, self.A = int(n_inst), int(n_steps), int(S), int(A)
+        self.params = params or _abi.Params()
+        self.r_dtype, self.out_dtype = r_dtype, out_dtype
+        self.want_overall, self.want_stats, self.variant = want_overall, want_stats, int(variant)
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        shp = (self.n_inst, self.n_steps)
+        e = lambda s, d: torch.empty(s, dtype=d, device=self.device)
+        self.value = e(shp, out_dtype)
+        self.act = e(shp, torch.int32)
+        self.overall = e(shp, out_dtype) if want_overall else None
+        self.activation_step = e((self.n_inst, self.S), torch.int64)
+        self.act_hist = torch.zeros(self.A, dtype=torch.int64, device=self.device) if want_stats else None
+        self.bad_rows = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.stats = e((STATS_HEADER + self.A,), torch.float64) if want_stats else None
+        L = _abi.lib()
+        need = L.dcarl_stream_bounds_ws(self.n_inst, self.n_steps, self.S, self.A) if self.variant == 1 else 0
+        self.ws = e((max(need, 16),), torch.uint8)
+        self._ws_bytes = need
+        self._pinned = None
+
+    # -- device path -------------------------------------------------------------------------
+    def run_device(self, idx, act, R, stream=None, check=False):
+        """idx/act int32, R r_dtype: CUDA tensors [n_inst, n_steps].  Asynchronous."""
+        L = _abi.lib()
+        for t, d in ((idx, torch.int32), (act, torch.int32), (R, self.r_dtype)):
+            if not (t.is_cuda and t.dtype == d and t.is_contiguous() and tuple(t.shape) == (self.n_inst, self.n_steps)):
+                raise ValueError("run_device: expected contiguous CUDA tensors [n_inst, n_steps] of int32/int32/R dtype")
+        sh = _dev.stream_handle(stream)
+        if self.want_stats:
+            self.act_hist.zero_()
+        self.bad_rows.zero_()
+        _abi.check(L.dcarl_stream_bounds(
+            _dev.ptr(idx), _dev.ptr(act), _dev.ptr(R), int(self.r_dtype == torch.float64),
+            self.n_inst, self.n_steps, self.S, self.A, self.params,
+            _dev.ptr(self.value), int(self.out_dtype == torch.float64), _dev.ptr(self.act),
+            _dev.ptr(self.activation_step), _dev.ptr(self.overall), _dev.ptr(self.act_hist),
+            _dev.ptr(self.bad_rows), _dev.ptr(self.ws), self._ws_bytes, self.variant, sh))
+        if self.want_stats:
+            _abi.check(L.dcarl_stream_stats(
+                _dev.ptr(self.value), int(self.out_dtype == torch.float64), _dev.ptr(self.overall),
+                _dev.ptr(self.activation_step), _dev.ptr(self.act_hist), self.n_inst, self.n_steps,
+                self.S, self.A, _dev.ptr(self.stats), sh))
+        if check:
+            self.raise_on_bad_rows()
+        return StreamResult(self.value, self.act, self.activation_step, self.overall, self.act_hist, self.stats)
+
+    def raise_on_bad_rows(self):
+        n = int(self.bad_rows.item())
+        if n:
+            raise IndexError(f"{n} rows have idx outside [0, {self.S}) or act outside [0, {self.A}) "
+                             "(the reference raises IndexError on such a row)")
+
+    # -- host path: pinned staging, copies inside --------------------------------------------
+    def _pin(self):
+        if self._pinned is None:
+            shp = (self.n_inst, self.n_steps)
+            pe = lambda d: torch.empty(shp, dtype=d).pin_memory()
+            self._pinned = dict(idx=pe(torch.int32), act=pe(torch.int32), R=pe(self.r_dtype),
+                                value=pe(self.out_dtype), oact=pe(torch.int32),
+                                overall=pe(self.out_dtype) if self.want_overall else None,
+                                astep=torch.empty((self.n_inst, self.S), dtype=torch.int64).pin_memory())
+            e = lambda d: torch.empty(shp, dtype=d, device=self.device)
+            self._din = (e(torch.int32), e(torch.int32), e(self.r_dtype))
+        return self._pinned
+
+    def h2d_bytes(self):
+        return self.n_inst * self.n_steps * (8 + (8 if self.r_dtype == torch.float64 else 4))
+
+    def d2h_bytes(self):
+        w = 8 if self.out_dtype == torch.float64 else 4
+        return self.n_inst * self.n_steps * (4 + w * (2 if self.want_overall else 1)) + self.n_inst * self.S * 8
+
+    def run_pinned(self, stream=None):
+        """Inputs already in the plan's pinned host buffers (``plan.pinned()['idx'|'act'|'R']``):
+        H2D, kernel, D2H of every output on one stream; returns after the stream has drained."""
+        pin = self._pin()
+        st = stream or torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            for d, h in zip(self._din, (pin["idx"], pin["act"], pin["R"])):
+                d.copy_(h, non_blocking=True)
+            self.run_device(*self._din, stream=st)
+            pin["value"].copy_(self.value, non_blocking=True)
+            pin["oact"].copy_(self.act, non_blocking=True)
+            if self.want_overall:
+                pin["overall"].copy_(self.overall, non_blocking=True)
+            pin["astep"].copy_(self.activation_step, non_blocking=True)
+        st.synchronize()
+        return pin
+
+    def pinned(self):
+        return self._pin()
+
+    def run_host(self, idx, act, R):
+        """numpy [n_inst, n_steps] in, numpy out."""
+        pin = self._pin()
+        pin["idx"].numpy()[...] = idx
+        pin["act"].numpy()[...] = act
+        pin["R"].numpy()[...] = R
+        self.run_pinned()
+        self.raise_on_bad_rows()
+        return StreamResult(pin["value"].numpy().copy(), pin["oact"].numpy().copy(), pin["astep"].numpy().copy(),
+                            pin["overall"].numpy().copy() if self.want_overall else None,
+                            self.act_hist.cpu().numpy() if self.want_stats else None,
+                            self.stats.cpu().numpy() if self.want_stats else None)
+
+
+def stream_bounds(idx, act, R, S, A, params=None, *, want_overall=True, out_dtype=None, variant=0,
+                  want_stats=False):
+    """One-shot batched call.  idx/act/R: [n_steps] or [n_inst, n_steps]; numpy (host) or CUDA tensors.
+
+    R float32 computes from float32 returns, anything else from float64; out_dtype defaults to
+    float64 unless R is float32.  Raises IndexError when a row's idx/act is out of range."""
+    _dev.require_cuda()
+    on_device = _dev.is_device(R)
+    r_dt = _dev.float_dtype_of(R)
+    o_dt = out_dtype or (torch.float32 if r_dt == torch.float32 else torch.float64)
+    if isinstance(o_dt, np.dtype) or o_dt in (np.float32, np.float64):
+        o_dt = torch.float32 if np.dtype(o_dt) == np.float32 else torch.float64
+    di, da, dr = _dev.as_device(idx, torch.int32), _dev.as_device(act, torch.int32), _dev.as_device(R, r_dt)
+    single = di.dim() == 1
+    if single:
+        di, da, dr = di[None], da[None], dr[None]
+    n_inst, n_steps = di.shape
+    plan = StreamPlan(n_inst, n_steps, S, A, params, r_dtype=r_dt, out_dtype=o_dt, want_overall=want_overall,
+                      want_stats=want_stats, variant=variant, device=di.device)
+    res = plan.run_device(di.contiguous(), da.contiguous(), dr.contiguous(), check=True)
+    sq = (lambda t: t[0]) if single else (lambda t: t)
+    conv = (lambda t: t) if on_device else (lambda t: t.cpu().numpy())
+    f = lambda t: None if t is None else conv(sq(t))
+    return StreamResult(f(res.value), f(res.act), f(res.activation_step), f(res.overall),
+                        None if res.act_hist is None else conv(res.act_hist),
+                        None if res.stats is None else conv(res.stats))
+
+
+def simulate(data, true_action_values, state_num, action_num, rule_act=0, n_thres=10, n_rows=20000):
+    """The body of test_DCARL.py as a function (ST1:33-99 / ST2:32-105).
+
+    data: float64 [N, 4] rows [idx, state, act, R] (``np.load('.../data.npy')``); the first n_rows
+    are streamed like ``data[0:20000]``.  Returns the script's globals: per-state lists
+    step_TSRL_value / step_TSRL_act / true_step_TSRL_value, activation_step, overall_value."""
+    data = np.asarray(data, np.float64)[:n_rows]
+    idx = data[:, 0].astype(np.int32)
+    act = data[:, 2].astype(np.int32)
+    res = stream_bounds(idx, act, data[:, 3], state_num, action_num,
+                        _abi.Params(rule_act=rule_act, n_thres=n_thres), want_overall=True)
+    tav = np.asarray(true_action_values)
+    by_state = [np.nonzero(idx == s)[0] for s in range(state_num)]
+    return dict(
+        step_TSRL_value=[res.value[r].tolist() for r in by_state],
+        step_TSRL_act=[res.act[r].astype(np.int64).tolist() for r in by_state],
+        true_step_TSRL_value=[tav[s][res.act[r]].tolist() for s, r in enumerate(by_state)],
+        activation_step=res.activation_step.copy(),
+        overall_value=res.overall.tolist(),
+        step_value_rows=res.value, step_act_rows=res.act)

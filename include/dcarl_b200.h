@@ -1,0 +1,161 @@
+/*
+ * dcarl_b200.h — C ABI of libdcarl_b200.so: the B200 (sm_100a) implementation of DCARL's
+ * data-parallel hot path.  The reference (zhcao92/DCARL) has no FFI of its own — the path
+ * is plain Python — so each entry point below names the reference
+ * function(s) it replaces; INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Reference files (relative to the reference repository root):
+ *   ST1 = Simulation_testing/Simulation_1/test_DCARL.py
+ *   ST2 = Simulation_testing/Simulation_2/test_DCARL.py
+ *   DS  = Simulation_testing/Simulation_Data_Collection/Data_Sampling/data_sampling.py
+ *   RLS = Field_testing/Software_and_Raw_Data_on_Self-Driving_Vehicle/software/src/tools/DCARL/
+ *         stable_baselines/deepq/RLS.py
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Unless a parameter says "host", every pointer is
+ *     a caller-owned DEVICE pointer on the current CUDA device.  No hidden allocation: calls
+ *     that need scratch take (ws, ws_bytes) sized by the matching *_ws() query.
+ *   - every compute call takes a cudaStream_t (passed as void*) and is asynchronous on it.
+ *   - return value: 0 = ok; < 0 = invalid argument (-(1-based argument index));
+ *     > 0 = cudaError_t of the failing runtime call / launch.
+ *     dcarl_last_error() returns a thread-local, human-readable description.
+ *   - re-entrant; no global mutable state besides the per-thread error string.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns an error.
+ */
+#ifndef DCARL_B200_H
+#define DCARL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCARL_B200_ABI_VERSION 1
+
+typedef void *dcarl_stream_t; /* cudaStream_t */
+
+/* Constants of the bound estimator.  Defaults are the literals of ST1:10-12, 43-52. */
+typedef struct dcarl_params {
+    double alpha;            /* ST1:10  0.05 */
+    double scale;            /* ST1:10  150  */
+    double cap;              /* ST1:12  min(100, .) on the rule action */
+    double prior_rule;       /* ST1:52  100  */
+    double prior_other;      /* ST1:51  -50  */
+    double activation_bonus; /* ST2:103 "- activation_value[i]*0.9", activation_value == -1 -> +0.9 */
+    int32_t n_thres;         /* ST1:45  10, the cell refreshes when len > n_thres (strict) */
+    int32_t rule_act;        /* ST1:43  0   */
+} dcarl_params;
+
+/* Constants of RLS.act_test (RLS:120-157) as constructed by dqn.py:106-112. */
+typedef struct dcarl_rls_params {
+    double rule_mean_gate;        /* RLS:141  -0.1 : skip when mean_rule > gate */
+    double confidence_thres;      /* RLS:120  0.5  */
+    int32_t visited_times_thres;  /* RLS:141  rule action needs >= this many visits (10 as deployed) */
+    int32_t min_candidate_visits; /* RLS:141  5 */
+} dcarl_rls_params;
+
+const char *dcarl_last_error(void);
+int dcarl_abi_version(void);
+/* Fills the current device's SM count and compute capability (host pointers). */
+int dcarl_device_info(int *sm_count, int *cc_major, int *cc_minor);
+void dcarl_default_params(dcarl_params *p);          /* host pointer */
+void dcarl_default_rls_params(dcarl_rls_params *p);  /* host pointer */
+
+/* ---- a1-a4: upper_bound / lower_bound / CI_lower_bound / mean_value, ST1:10-28 -----------
+ * Segmented: sample array `seg` occupies x[seg_offsets[seg] .. seg_offsets[seg+1]).
+ * out[seg*4 + {0,1,2,3}] = {upper_bound, lower_bound, CI_lower_bound, mean_value}; an empty
+ * segment yields NaN (numpy: mean of an empty array).  Two-pass mean / population std in
+ * float64 like np.mean / np.std.  x is float64 (x_is_f64 != 0) or float32. */
+int dcarl_bounds(const void *x, int x_is_f64, const int64_t *seg_offsets, int64_t n_seg,
+                 const dcarl_params *p /* host */, double *out, dcarl_stream_t stream);
+
+/* ---- a5-a7: the streaming estimator + argmax selector, ST1:73-99 / ST2:72-105 ------------
+ * n_inst independent scenario instances, each a stream of n_steps rows {idx, act, R}.
+ * Layout: row-major [n_inst, n_steps] for idx (int32, 0 <= idx < S), act (int32, 0 <= act < A)
+ * and R (float32, or float64 when r_is_f64).  Per row k of instance i the kernel appends R to
+ * cell (idx, act), refreshes that cell's bound once it holds more than n_thres samples
+ * (rule action: upper bound; others: min(lower, CI lower)), and emits
+ *   out_value[i,k] = max_a value[idx][a]          (float32, or float64 when out_is_f64)
+ *   out_act[i,k]   = argmax_a value[idx][a]       (first maximum, like np.argmax)
+ *   out_overall[i,k] (nullable) = sum over activated states of (max + activation_bonus), ST2:99-105
+ *   out_activation_step[i,s] = per-state 1-based step at which argmax first left rule_act, else -1
+ *   act_hist[A] (nullable, uint64, ACCUMULATED into) = histogram of out_act over all rows.
+ * Rows with idx/act out of range poison nothing: they are counted in *bad_rows (nullable,
+ * uint64, accumulated) and emit value = NaN, act = -1.
+ * variant: 0 = default (row-parallel shared-memory kernel when the S*A table fits in shared
+ * memory, else the global-memory walker), 1 = force the walker (needs ws), 2 = force the
+ * row-parallel kernel (error if it does not fit).
+ */
+size_t dcarl_stream_bounds_ws(int64_t n_inst, int64_t n_steps, int32_t S, int32_t A);
+int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const void *R, int r_is_f64,
+                        int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
+                        const dcarl_params *p /* host */,
+                        void *out_value, int out_is_f64, int32_t *out_act,
+                        int64_t *out_activation_step, void *out_overall,
+                        uint64_t *act_hist, uint64_t *bad_rows,
+                        void *ws, size_t ws_bytes, int variant, dcarl_stream_t stream);
+
+/* Summary statistics of one batch, the vector that is all-reduced across GPUs:
+ * stats[0] = sum_i out_value[i, n_steps-1]       stats[1] = sum_i out_overall[i, n_steps-1] (0 if null)
+ * stats[2] = # activated (instance,state) pairs  stats[3] = sum of their activation_step
+ * stats[4] = n_inst*n_steps                      stats[5+a] = act_hist[a]  (0 if act_hist null)
+ * Fixed-order float64 reduction: bitwise reproducible for a given input. */
+#define DCARL_STATS_HEADER 5
+int dcarl_stream_stats(const void *out_value, int out_is_f64, const void *out_overall,
+                       const int64_t *out_activation_step, const uint64_t *act_hist,
+                       int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
+                       double *stats /* [DCARL_STATS_HEADER + A] */, dcarl_stream_t stream);
+
+/* ---- a8: the {s,a,R} sampler of Data_Generation, DS:12-17, 45-55 -------------------------
+ * Draw i: x = loc + sd*z_state[i]; idx = floor(x/span*S); rejected (out_idx = -1, R = 0) when
+ * idx is outside [0,S) (DS:50-51); else R = q_star[idx, act[i]] + sigma*z_ret[i] (DS:9, 55).
+ * z_state / z_ret are standard normal deviates supplied by the caller (float32, or float64 when
+ * z_is_f64); arithmetic is float64; out_R is float32 (float64 when out_is_f64). */
+int dcarl_sample_returns(const void *q_star, int q_is_f64, const void *z_state, const void *z_ret,
+                         int z_is_f64, const int32_t *act, int64_t n, int32_t S, int32_t A,
+                         double loc, double sd, double span, double sigma,
+                         int32_t *out_idx, void *out_R, int out_is_f64, dcarl_stream_t stream);
+/* Same draw with on-device Philox4x32-10 + Box-Muller deviates and uniform actions; row i uses
+ * counter (i, 0, 0, 0) and key (seed_lo, seed_hi): reproducible for any grid shape. */
+int dcarl_sample_returns_philox(const void *q_star, int q_is_f64, uint64_t seed, int64_t n,
+                                int32_t S, int32_t A, double loc, double sd, double span,
+                                double sigma, int32_t *out_idx, int32_t *out_act, void *out_R,
+                                int out_is_f64, dcarl_stream_t stream);
+
+/* ---- a9-a11: box-kernel confidence, RLS:161-181 and RLS.act_test, RLS:120-157 ------------
+ * Buffer: M stored rows, buf_state float32 [M, D+1] (D observation dims, then the action),
+ * buf_ret float32 [M] (the return, column 1 of visited_value, RLS:174).  Row i covers the
+ * closed box [s_i - dist, s_i + dist] evaluated in float64 (RLS:195-196); a query point
+ * obs (+) a (RLS:91-93) matches the rows whose box contains it.  For each of the Q queries
+ * (float64 [Q, D]) and each candidate action a in [0, n_actions) writes the raw moments
+ * out_moments[q, a, {0,1,2}] = {n, sum R, sum R^2} (float64; zeroed by the call).
+ * The kernel is one streaming pass over the buffer: 4*(D+2) bytes per row, independent of Q. */
+size_t dcarl_box_moments_ws(int32_t Q, int32_t D, int32_t n_actions);
+int dcarl_box_moments(const float *buf_state, const float *buf_ret, int64_t M, int32_t D,
+                      const double *dist /* [D+1] */, const double *queries /* [Q, D] */,
+                      int32_t Q, int32_t n_actions, double *out_moments,
+                      void *ws, size_t ws_bytes, dcarl_stream_t stream);
+/* Moments -> (mean, var) with the (-1,-1) sentinel for n == 0 (RLS:169-170) and the
+ * act_test pick: first candidate 1..n_actions-1 passing the gate and the z-test, else 0.
+ * out_mean_var [Q, n_actions, 2] and out_action [Q] are each nullable. */
+int dcarl_box_select(const double *moments, int32_t Q, int32_t n_actions,
+                     const dcarl_rls_params *p /* host */, double *out_mean_var,
+                     int32_t *out_action, dcarl_stream_t stream);
+
+/* ---- a14: constant-velocity rollout surrogate (CARLA itself is external) -----
+ * state0 float32 [n, 20] = ego + 3 objects x [x, y, vx, vy, yaw]; the ego velocity is scaled
+ * by speed_scale[action]; every step advances all four bodies by v*dt, a collision
+ * (squared distance <= radius^2) ends the episode with -100, passing pass_x ends it, else the
+ * step reward 0.1*sqrt(|v_ego|) accrues.  out_term: 0 horizon, 1 collision, 2 pass. */
+int dcarl_rollout_cv(const float *state0, const int32_t *action, int64_t n, int32_t steps,
+                     float dt, float radius, float pass_x, const float *speed_scale,
+                     int32_t n_actions, float *out_return, int32_t *out_steps, int32_t *out_term,
+                     dcarl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCARL_B200_H */

@@ -1,0 +1,182 @@
+"""Parity of the box-kernel confidence path (RLS.py:120-181) with the logged field queries and
+the oracle: visit counts and the picked action bit-exact, mean/var within 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dcarl_b200 as dc
+from dcarl_b200 import _abi
+from oracle import cport, pyref
+
+pytestmark = pytest.mark.gpu
+DIST = dc.VISITED_STATE_DIST[0]
+
+
+def _f32(x):
+    return np.asarray(x, np.float32).astype(np.float64)
+
+
+def _oracle_nmv(vs, ret, queries, n_actions, dist=DIST):
+    """oracle on the SAME inputs the device holds (float32 buffer widened to float64)."""
+    return cport.box_moments(_f32(vs), _f32(ret), dist, queries, n_actions)
+
+
+def _check(buf, vs, ret, queries, n_actions, rls=None, dist=DIST):
+    n, mean, var, pick = buf.query(queries, n_actions, rls)
+    ref = _oracle_nmv(vs, ret, queries, n_actions, dist)
+    assert np.array_equal(n, ref[:, :, 0])                                  # visited times: exact
+    assert np.abs(mean - ref[:, :, 1]).max() < 1e-9 and np.abs(var - ref[:, :, 2]).max() < 1e-9
+    kw = {} if rls is None else dict(visited_times_thres=rls.visited_times_thres, confidence_thres=rls.confidence_thres)
+    assert np.array_equal(pick, cport.box_select(ref, **kw))
+    return n, mean, var, pick
+
+
+def test_logged_field_queries(golden):
+    g = golden("rls_box")
+    vs, vv, dr = g["visited_state"], g["visited_value"], g["driving_record"]
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, vv[:, 1])
+    n, mean, var, pick = _check(buf, vs, vv[:, 1], dr[:, :20], 8)
+    assert np.array_equal(n[:, 0], dr[:, 23])                               # 107 / 107 logged counts
+    assert np.abs(mean[:, 0] - dr[:, 24]).max() < 1e-5 and np.abs(var[:, 0] - dr[:, 25]).max() < 1e-5
+    # one query at a time gives the same answer as the batch
+    n1, m1, v1, p1 = buf.query(dr[17, :20], 8)
+    assert np.array_equal(n1[0], n[17]) and p1[0] == pick[17]
+
+
+def _clustered(rng, n_centers=6, n_actions=8, max_rows=40, D=20):
+    centers = rng.normal(0, 1, (n_centers, D)) * DIST[:D]
+    rows, vals = [], []
+    for c in centers:
+        for a in range(n_actions):
+            m = int(rng.integers(0, max_rows))
+            s = c + rng.uniform(-0.45, 0.45, (m, D)) * DIST[:D]
+            rows.append(np.hstack([s, np.full((m, 1), float(a))]))
+            vals.append(-0.95 ** rng.integers(0, 10, m) * (rng.random(m) < (0.3 + 0.08 * a)))
+    return centers, np.vstack(rows), np.concatenate(vals)
+
+
+def test_candidate_branch_and_literal_port():
+    rng = np.random.default_rng(11)
+    centers, vs, ret = _clustered(rng)
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, ret)
+    n, mean, var, pick = _check(buf, vs, ret, centers, 8)
+    assert pick.max() > 0
+    lit = pyref.BoxBuffer(_f32(vs), np.stack([vs[:, 20], _f32(ret)], 1))
+    for qi, c in enumerate(centers):
+        assert int(lit.act_test(c)) == pick[qi]
+    # a stricter confidence threshold goes through Phi(z)
+    rp = _abi.RlsParams(confidence_thres=0.9, visited_times_thres=3)
+    _check(buf, vs, ret, centers, 8, rp)
+
+
+@pytest.mark.parametrize("M", [0, 1, 255, 256, 257, 1000, 4099])
+def test_ragged_buffer_sizes(M):
+    rng = np.random.default_rng(M)
+    _, vs, ret = _clustered(rng, n_centers=3, max_rows=200)
+    vs, ret = vs[:M], ret[:M]
+    buf = dc.BoxBuffer(20, capacity=16)
+    if M:
+        buf.append(vs, ret)
+    q = vs[rng.integers(0, max(M, 1), 5), :20] if M else np.zeros((5, 20))
+    _check(buf, vs.reshape(-1, 21), ret, q, 8)
+
+
+def test_closed_box_faces_and_float32_threshold_walk():
+    """Stored rows exactly on, just inside and just outside a face of the query box."""
+    rng = np.random.default_rng(5)
+    q = (rng.normal(0, 3, 20)).astype(np.float32).astype(np.float64)
+    rows = []
+    for d in range(20):
+        for sign in (-1.0, 1.0):
+            face = np.float32(q[d] + sign * DIST[d])
+            for s in (face, np.nextafter(face, np.float32(np.inf)), np.nextafter(face, np.float32(-np.inf))):
+                r = q.copy()
+                r[d] = s
+                rows.append(np.append(r, 0.0))
+    vs = np.asarray(rows)
+    ret = -rng.random(len(vs))
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, ret)
+    n, *_ = _check(buf, vs, ret, q[None], 4)
+    assert 0 < n[0, 0] < len(vs)
+
+
+def test_many_queries_many_candidates_and_non_integer_actions():
+    rng = np.random.default_rng(8)
+    M, Q, NA = 20000, 64, 256
+    base = rng.normal(0, 1, (40, 20)) * DIST[:20]
+    vs = base[rng.integers(0, 40, M)] + rng.normal(0, 0.3, (M, 20)) * DIST[:20]
+    acts = rng.integers(0, NA, M).astype(np.float64)
+    acts[::97] += 0.05                 # inside the +-0.1 action tolerance
+    acts[::89] += 0.3                  # outside: matches no candidate
+    vs = np.hstack([vs, acts[:, None]])
+    ret = -rng.random(M)
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, ret)
+    queries = base[rng.integers(0, 40, Q)] + rng.normal(0, 0.1, (Q, 20)) * DIST[:20]
+    n, *_ = _check(buf, vs, ret, queries, NA)
+    assert n.sum() > 0
+    # a wide action tolerance lets one stored row count for several candidates (general rtree semantics)
+    wide = DIST.copy()
+    wide[20] = 1.0
+    buf2 = dc.BoxBuffer(20, dist=wide)
+    buf2.append(vs[:3000], ret[:3000])
+    _check(buf2, vs[:3000], ret[:3000], queries[:4], 16, dist=wide)
+
+
+def test_other_dimensions_use_the_generic_kernel():
+    rng = np.random.default_rng(13)
+    D = 6
+    dist = np.array([1, 0.5, 2, 3, 0.25, 4, 0.1])
+    vs = np.hstack([rng.normal(0, 1, (5000, D)), rng.integers(0, 4, (5000, 1)).astype(np.float64)])
+    ret = rng.normal(0, 1, 5000)
+    buf = dc.BoxBuffer(D, dist=dist)
+    buf.append(vs, ret)
+    q = rng.normal(0, 0.5, (9, D))
+    n, mean, var, _ = buf.query(q, 4)
+    ref = cport.box_moments(_f32(vs), _f32(ret), dist, q, 4)
+    assert np.array_equal(n, ref[:, :, 0]) and np.abs(mean - ref[:, :, 1]).max() < 1e-9
+    assert np.abs(var - ref[:, :, 2]).max() < 1e-9
+
+
+def test_rls_class_drop_in(tmp_path, golden, monkeypatch):
+    """Constructor loads visited_*.txt from the cwd, act/act_test answer like the logged run,
+    add_data appends lagged / terminal-discounted returns (RLS.py:185-215)."""
+    g = golden("rls_box")
+    vs, vv, dr = g["visited_state"], g["visited_value"], g["driving_record"]
+    monkeypatch.chdir(tmp_path)
+    np.savetxt("visited_state.txt", vs, fmt="%f")
+    np.savetxt("visited_value.txt", vv, fmt="%f")
+    rls = dc.RLS(visited_times_thres=10, is_training=False, debug=False, save_new_data=True,
+                 create_new_train_file=False, create_new_record_file=True, save_new_driving_data=True)
+    assert rls.visited_state_counter == len(vs)
+    for qi in (0, 50, 106):
+        obs = dr[qi, :20]
+        rule = rls.state_with_action(obs, 0)
+        assert rls._calculate_visited_times(rule, rls.visited_state_tree) == int(dr[qi, 23])
+        mean, var, sigma = rls._calculate_statistics_index(rule, rls.visited_state_value, rls.visited_state_tree)
+        assert abs(mean - dr[qi, 24]) < 1e-5 and abs(var - dr[qi, 25]) < 1e-5 and abs(sigma - np.sqrt(var)) < 1e-12
+        a = rls.act(obs, np.array(3))
+        assert isinstance(a, np.ndarray) and a.shape == () and int(a) == 0
+    # unseen observation: the sentinel
+    far = np.full(20, 1e4)
+    assert rls._calculate_statistics_index(rls.state_with_action(far, 2)) == (-1, -1, -1)
+    # add_data: 14 quiet steps then a collision; 15 new rows with the discounted tail
+    before = len(rls.visited_state_tree)
+    for t in range(15):
+        rls.add_data(far + t, 1, 0.0 if t < 14 else -1.0, far + t + 1, t == 14)
+    assert len(rls.visited_state_tree) == before + 15
+    tail = rls.visited_state_tree.ret[before:].cpu().numpy()
+    want = np.array([r for _, r in pyref.add_data_returns([0.0] * 14 + [-1.0], [False] * 14 + [True])], np.float32)
+    assert np.array_equal(tail, want)
+    rls.visited_state_outfile.flush(); rls.driving_record_outfile.flush()
+    assert len(open("visited_state.txt").readlines()) == len(vs) + 15
+    rec = np.loadtxt("driving_record.txt")
+    assert rec.shape == (15, 29)
+    # should_use_rule: under-visited rule action -> rule
+    rls.is_training = True
+    assert int(rls.act(far, np.array(5))) == 0

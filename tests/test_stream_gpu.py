@@ -1,0 +1,174 @@
+"""Parity of the CUDA stream kernels (through the C ABI) with the oracle and the reference's
+golden outputs.  Integer outputs (argmax, activation step) bit-exact; values within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import dcarl_b200 as dc
+from dcarl_b200 import _abi
+from oracle import cport
+from helpers import compare_stream, recompute_from_traces, stats_reference, synth_streams
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(idx, act, R, S, A, **kw):
+    return cport.stream(idx, act, np.asarray(R, np.float64), S, A, cport.default_params(**kw))
+
+
+@pytest.mark.parametrize("which", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_golden_reference_traces(golden, which, variant):
+    g = golden(f"sim{which}")
+    S, A, N = int(g["S"]), int(g["A"]), int(g["n_rows"])
+    res = dc.stream_bounds(g["idx"][:N].astype(np.int32), g["act"][:N].astype(np.int32), g["R"][:N], S, A,
+                           variant=variant)
+    assert res.value.dtype == np.float64
+    assert np.array_equal(res.act, g["step_act"])                      # bit-exact argmax, 20 000 rows
+    assert np.array_equal(res.activation_step, g["activation_step"])
+    assert np.abs(res.value - g["step_value"]).max() < 1e-9
+    if "overall_value" in g.files:
+        assert np.abs(res.overall - g["overall_value"]).max() < 1e-8
+
+
+def test_simulate_mirrors_the_script_globals(golden):
+    g = golden("sim2")
+    N = int(g["n_rows"])
+    data = np.stack([g["idx"], g["state"], g["act"], g["R"]], axis=1).astype(np.float64)
+    out = dc.simulate(data, g["true_action_values"], 20, 11)
+    idx = g["idx"][:N]
+    for s in range(20):
+        rows = np.nonzero(idx == s)[0]
+        assert out["step_TSRL_act"][s] == g["step_act"][rows].tolist()
+        assert out["true_step_TSRL_value"][s] == g["true_step_value"][rows].tolist()
+        assert np.allclose(out["step_TSRL_value"][s], g["step_value"][rows], rtol=0, atol=1e-9)
+    assert out["activation_step"].tolist() == g["activation_step"].tolist()
+    assert abs(out["overall_value"][-1] - 597.7193818873668) < 1e-8
+
+
+SHAPES = [
+    # n_inst, n_steps, S, A, params
+    (48, 2500, 20, 11, {}),
+    (33, 1999, 1, 30, {}),                       # Sim-1 shape, ragged tail
+    (7, 31, 20, 11, {}),                         # shorter than one batch
+    (5, 700, 3, 40, {}),                         # A > 32
+    (5, 900, 40, 5, {"rule_act": 3}),            # S > 32, rule action moved
+    (6, 800, 4, 6, {"n_thres": 0}),              # refresh from the first sample
+    (6, 800, 4, 6, {"prior_other": 100.0}),      # priors tie with the rule action
+    (4, 600, 2, 3, {"alpha": 0.2, "scale": 40.0, "cap": 60.0, "activation_bonus": 2.5}),
+]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_random_instances_vs_oracle_f64(shape, variant):
+    n_inst, n_steps, S, A, kw = shape
+    idx, act, R = synth_streams(n_inst, n_steps, S, A, seed=7 + n_steps, r_dtype=np.float64)
+    res = dc.stream_bounds(idx, act, R, S, A, _abi.Params(**kw), variant=variant)
+    compare_stream(res, _oracle(idx, act, R, S, A, **kw), value_tol=1e-9)
+
+
+def test_float32_inputs_and_outputs():
+    idx, act, R = synth_streams(40, 3000, 20, 11, seed=99, r_dtype=np.float32)
+    ref = _oracle(idx, act, R.astype(np.float64), 20, 11)           # same inputs, widened
+    res = dc.stream_bounds(idx, act, R, 20, 11)                        # float32 in -> float32 out
+    assert res.value.dtype == np.float32 and res.overall.dtype == np.float32
+    compare_stream(res, ref, value_tol=1e-5)
+    res64 = dc.stream_bounds(idx, act, R, 20, 11, out_dtype=torch.float64)
+    compare_stream(res64, ref, value_tol=1e-9)
+
+
+def test_integer_returns_make_exact_ties():
+    rng = np.random.default_rng(3)
+    n_inst, n_steps, S, A = 16, 1500, 3, 5
+    idx = rng.integers(0, S, (n_inst, n_steps)).astype(np.int32)
+    act = rng.integers(0, A, (n_inst, n_steps)).astype(np.int32)
+    R = np.round(rng.normal(40, 3, (n_inst, n_steps)) / 20) * 20       # few distinct values -> equal cells
+    for variant in (0, 1):
+        res = dc.stream_bounds(idx, act, R, S, A, _abi.Params(n_thres=2), variant=variant)
+        compare_stream(res, _oracle(idx, act, R, S, A, n_thres=2), value_tol=1e-9, max_near_ties=0)
+
+
+def test_two_kernels_agree_bitwise_on_indices():
+    idx, act, R = synth_streams(64, 4000, 20, 11, seed=5, r_dtype=np.float32)
+    a = dc.stream_bounds(idx, act, R, 20, 11, variant=2, out_dtype=torch.float64)
+    b = dc.stream_bounds(idx, act, R, 20, 11, variant=1, out_dtype=torch.float64)
+    assert np.array_equal(a.act, b.act) and np.array_equal(a.activation_step, b.activation_step)
+    assert np.abs(a.value - b.value).max() < 1e-10 and np.abs(a.overall - b.overall).max() < 1e-8
+
+
+def test_empty_and_invalid_inputs():
+    z = np.zeros((3, 0), np.int32)
+    res = dc.stream_bounds(z, z, np.zeros((3, 0)), 4, 5)
+    assert res.value.shape == (3, 0) and (res.activation_step == -1).all()
+    res = dc.stream_bounds(np.zeros((0, 10), np.int32), np.zeros((0, 10), np.int32), np.zeros((0, 10)), 4, 5)
+    assert res.value.shape == (0, 10)
+    idx, act, R = synth_streams(2, 100, 4, 5, seed=1, r_dtype=np.float64)
+    idx[1, 50] = 4                                                      # == S: out of range
+    with pytest.raises(IndexError):
+        dc.stream_bounds(idx, act, R, 4, 5)
+    with pytest.raises(dc.DcarlError):
+        dc.stream_bounds(idx, act, R, 4, 5, _abi.Params(rule_act=9))
+
+
+def test_device_tensors_in_device_tensors_out_and_stats():
+    idx, act, R = synth_streams(96, 2048, 20, 11, seed=21, r_dtype=np.float32)
+    plan = dc.StreamPlan(96, 2048, 20, 11)
+    d = [torch.from_numpy(x).cuda() for x in (idx, act, R)]
+    res = plan.run_device(*d)
+    assert res.value.is_cuda and res.act.dtype == torch.int32
+    torch.cuda.synchronize()
+    v, a, o, st = res.value.cpu().numpy(), res.act.cpu().numpy(), res.overall.cpu().numpy(), res.activation_step.cpu().numpy()
+    want = stats_reference(v, o, st, a, 11)
+    got = res.stats.cpu().numpy()
+    assert np.array_equal(got[2:], want[2:])                            # counts and histogram: exact
+    assert np.allclose(got[:2], want[:2], rtol=1e-12)
+    assert np.array_equal(res.act_hist.cpu().numpy(), np.bincount(a.ravel(), minlength=11))
+    # the pinned host path returns the same bits
+    h = plan.run_host(idx, act, R)
+    assert np.array_equal(h.value, v) and np.array_equal(h.act, a) and np.array_equal(h.overall, o)
+    # a second run of the same plan is bitwise reproducible (no order-dependent atomics on outputs)
+    res2 = plan.run_device(*d)
+    torch.cuda.synchronize()
+    assert torch.equal(res2.value, res.value) and torch.equal(res2.stats, res.stats)
+
+
+def test_full_size_config2_properties_and_sampled_parity():
+    """BASELINE config 2: 4096 instances x 20 000 steps, S=20, A=11, float32 rows."""
+    n_inst, n_steps, S, A = 4096, 20000, 20, 11
+    g = torch.Generator(device="cuda").manual_seed(2)
+    q = torch.rand((n_inst, S, A), generator=g, device="cuda") * 150 - 50
+    idx = torch.floor((3 + torch.randn((n_inst, n_steps), generator=g, device="cuda")) / 6 * S).clamp_(0, S - 1).to(torch.int32)
+    act = torch.randint(0, A, (n_inst, n_steps), generator=g, device="cuda", dtype=torch.int32)
+    R = q.reshape(n_inst, -1).gather(1, (idx.long() * A + act.long())) + 50 * torch.randn((n_inst, n_steps), generator=g, device="cuda")
+    del q
+    plan = dc.StreamPlan(n_inst, n_steps, S, A)
+    res = plan.run_device(idx, act, R)
+    torch.cuda.synchronize()
+    plan.raise_on_bad_rows()
+    a = res.act
+    assert int(a.min()) >= 0 and int(a.max()) < A
+    assert torch.equal(res.act_hist, torch.bincount(a.reshape(-1).long(), minlength=A))
+    assert bool(torch.isfinite(res.value).all()) and bool(torch.isfinite(res.overall).all())
+    # sharding invariance: the same instances run as two half batches give the same bits
+    half = dc.StreamPlan(n_inst // 2, n_steps, S, A)
+    for lo in (0, n_inst // 2):
+        sl = slice(lo, lo + n_inst // 2)
+        r2 = half.run_device(idx[sl].contiguous(), act[sl].contiguous(), R[sl].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(r2.value, res.value[sl]) and torch.equal(r2.act, res.act[sl])
+        assert torch.equal(r2.overall, res.overall[sl]) and torch.equal(r2.activation_step, res.activation_step[sl])
+    # sampled instances against the oracle, and the trace-derived consistency on a few
+    pick = np.random.default_rng(0).choice(n_inst, 24, replace=False)
+    pi = torch.from_numpy(pick).cuda()
+    hi, ha, hr = idx[pi].cpu().numpy(), act[pi].cpu().numpy(), R[pi].cpu().numpy()
+    class _R:
+        pass
+    sub = _R()
+    sub.value, sub.act = res.value[pi].cpu().numpy(), res.act[pi].cpu().numpy()
+    sub.overall, sub.activation_step = res.overall[pi].cpu().numpy(), res.activation_step[pi].cpu().numpy()
+    compare_stream(sub, _oracle(hi, ha, hr.astype(np.float64), S, A), value_tol=1e-5, max_near_ties=1)
+    for j in range(3):
+        astep, ov = recompute_from_traces(hi[j], sub.value[j].astype(np.float64), sub.act[j], S)
+        assert np.array_equal(astep, sub.activation_step[j])
+        assert np.abs(ov - sub.overall[j]).max() < 1e-2 * 1e-1   # float32 traces: 20 states x ~6e-6 each
