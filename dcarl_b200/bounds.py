@@ -63,3 +63,23 @@ def CI_lower_bound(data_array, alpha=0.05, loc=-50, scale=150):
 def mean_value(data_array, alpha=0.05, loc=-50, scale=150):
     """min(100, mean) — test_DCARL.py:26-28."""
     return _one(data_array, alpha, scale, 3)
+
+
+def cell_values(n, total, total_sq, act, *, alpha=0.05, scale=150, cap=100.0, rule_act=0):
+    """The bound of cells given their moments (count, sum, sum of squares) and action, evaluated by
+    the same device code the stream kernel uses: upper bound for ``act == rule_act``, else
+    min(lower, CI lower).  numpy in -> numpy out, CUDA tensors in -> CUDA tensor out."""
+    _dev.require_cuda()
+    on_device = _dev.is_device(total)
+    dn = _dev.as_device(n, torch.int32).reshape(-1)
+    d1 = _dev.as_device(total, torch.float64).reshape(-1)
+    d2 = _dev.as_device(total_sq, torch.float64).reshape(-1)
+    da = _dev.as_device(act, torch.int32).reshape(-1)
+    cnt = dn.numel()
+    if not (d1.numel() == d2.numel() == da.numel() == cnt):
+        raise ValueError("n, total, total_sq and act must have the same length")
+    out = _dev.empty((cnt,), torch.float64)
+    p = _abi.Params(alpha=alpha, scale=scale, cap=cap, rule_act=rule_act)
+    _abi.check(_abi.lib().dcarl_cell_values(_dev.ptr(dn), _dev.ptr(d1), _dev.ptr(d2), _dev.ptr(da), cnt, p,
+                                            _dev.ptr(out), _dev.stream_handle()))
+    return out if on_device else out.cpu().numpy()

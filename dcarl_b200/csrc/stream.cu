@@ -38,40 +38,60 @@ struct StreamArgs {
     void *out_overall;
     unsigned long long *act_hist;
     unsigned long long *bad_rows;
-    long long n_inst, n_steps;
+    long long n_inst;
+    unsigned n_steps;
     int S, A;
     double c_h;  // scale * sqrt(ln(1/alpha) / 2)
     double cap, prior_rule, prior_other, bonus;
     int n_thres, rule_act;
 };
 
+constexpr int kLut = 256;  // shared-memory table of {1/sqrt(n), 1/sqrt(n+1)} for n < kLut
+
 __device__ __forceinline__ double u32_to_double(unsigned n) {
     // exact for every uint32; avoids the slow I2F.F64 conversion path
     return __hiloint2double(0x43300000, (int)n) - 4503599627370496.0;
 }
 
-// Value of a cell holding n samples with sum s1 and sum of squares s2.
+// 1/sqrt(x) for positive, normal, finite x: hardware seed (MUFU.RSQ64H, ~2^-20) and one
+// third-order step y(1 + e/2 + 3e^2/8), e = 1 - x y^2; remaining error ~e^3 << 2^-53.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double q = fma(e, 0.375, 0.5);
+    return fma(y * e, q, y);
+}
+
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
+
+// Value of a cell holding n samples with sum s1 and sum of squares s2, given
+// rs = 1/sqrt(n) and rs1 = 1/sqrt(n+1).
 //   rule action:  min(cap, mean + scale*sqrt(L/2/n))                       ST1:12
 //   other:        min(mean - scale*sqrt(L/2/n),                            ST1:16
 //                     sum/n/(n+1) - 4*std/(n+1) + sum/(n+1) - scale*sqrt(L/2/(n+1)))   ST1:24
-// evaluated in float64 with one rsqrt per radicand (a few ulp from the reference's
-// divide/sqrt chain, far inside the 1e-5 value tolerance).
-__device__ __forceinline__ double cell_value(unsigned n, double s1, double s2, bool is_rule,
-                                             double c_h, double cap) {
-    const double dn = u32_to_double(n);
-    const double rs = rsqrt(dn);
+// evaluated in float64 (a few ulp from the reference's divide/sqrt chain, far inside
+// the 1e-5 value tolerance; the argmax only flips on ties closer than ~1e-11).
+__device__ __forceinline__ double cell_value_rs(double rs, double rs1, double s1, double s2, bool is_rule,
+                                                double c_h, double cap) {
     const double inv_n = rs * rs;
     const double hn = c_h * rs;
     const double mean = s1 * inv_n;
-    const double ub = fmin(cap, mean + hn);
-    const double rs1 = rsqrt(dn + 1.0);
+    const double ub = dmin(cap, mean + hn);
     const double inv_n1 = rs1 * rs1;
     const double hn1 = c_h * rs1;
     const double var = fma(s2, inv_n, -mean * mean);
-    const double sigma = var > 0.0 ? var * rsqrt(var) : 0.0;
+    const double sigma = var > 1e-280 ? var * rsqrt_pos(var) : 0.0;
     const double lb = mean - hn;
     const double ci = fma(fma(-4.0, sigma, mean) + s1, inv_n1, -hn1);
-    return is_rule ? ub : fmin(lb, ci);
+    return is_rule ? ub : dmin(lb, ci);
+}
+
+__device__ __forceinline__ double cell_value(unsigned n, double s1, double s2, bool is_rule, double c_h,
+                                             double cap) {
+    const double dn = u32_to_double(n);
+    return cell_value_rs(rsqrt_pos(dn), rsqrt_pos(dn + 1.0), s1, s2, is_rule, c_h, cap);
 }
 
 // Runner-up bound kept per state: any value in [second, max) keeps both fast-path
@@ -82,115 +102,143 @@ __device__ __forceinline__ double runner_up_bound(double second, double mx) {
     return 0.5 * second + 0.5 * mx;
 }
 
-// Warp-wide exact (max, first argmax, max of the rest) of row[0..A).
-__device__ __forceinline__ void warp_top2(const double *row, int A, double &mx, int &arg,
+// ---- exact warp-wide max of doubles with integer reductions (REDUX) ---------------------------
+// Order-preserving 64-bit key of a (non-NaN) double, split in two 32-bit halves.
+__device__ __forceinline__ void order_key(double x, unsigned &hi, unsigned &lo) {
+    x += 0.0;  // -0.0 -> +0.0 so that equal doubles get equal keys
+    const int h = __double2hiint(x);
+    const unsigned sgn = (unsigned)(h >> 31);
+    hi = (unsigned)h ^ (sgn | 0x80000000u);
+    lo = (unsigned)__double2loint(x) ^ sgn;
+}
+// Mask of the lanes holding the warp maximum of x.
+__device__ __forceinline__ unsigned warp_max_lanes(double x) {
+    unsigned hi, lo;
+    order_key(x, hi, lo);
+    const unsigned H = __reduce_max_sync(FULL_MASK, hi);
+    const bool top = hi == H;
+    const unsigned L = __reduce_max_sync(FULL_MASK, top ? lo : 0u);
+    return __ballot_sync(FULL_MASK, top && lo == L);
+}
+
+// Exact (max, first argmax, max of the rest) of row[0 .. A) with element stride `stride` doubles.
+__device__ __forceinline__ void warp_top2(const double *row, int stride, int A, double &mx, int &arg,
                                           double &second) {
     const int lane = lane_id();
     double bm = -CUDART_INF, b2 = -CUDART_INF;
     int bg = 0x7fffffff;
-    for (int a = lane; a < A; a += 32) {
-        const double c = row[a];
+    for (int a = lane; a < A; a += 32) {   // ascending a: a strict compare keeps the first index
+        const double c = row[(size_t)a * stride];
         if (c > bm) { b2 = bm; bm = c; bg = a; }
         else if (c > b2) b2 = c;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double om = __shfl_xor_sync(FULL_MASK, bm, off);
-        const double o2 = __shfl_xor_sync(FULL_MASK, b2, off);
-        const int og = __shfl_xor_sync(FULL_MASK, bg, off);
-        const bool better = om > bm || (om == bm && og < bg);
-        if (better) { b2 = fmax(bm, o2); bm = om; bg = og; }
-        else { b2 = fmax(b2, om); }
-    }
-    mx = bm; arg = bg; second = b2;
+    const unsigned win = warp_max_lanes(bm);
+    arg = __reduce_min_sync(FULL_MASK, ((win >> lane) & 1u) ? bg : 0x7fffffff);
+    const int wl = __ffs(__ballot_sync(FULL_MASK, ((win >> lane) & 1u) && bg == arg)) - 1;
+    mx = shfl_f64(bm, wl);
+    const double contrib = lane == wl ? b2 : bm;
+    const unsigned win2 = warp_max_lanes(contrib);
+    second = shfl_f64(contrib, __ffs(win2) - 1);
 }
+
+struct Cell {
+    double s1, s2, val;
+};
 
 __host__ __device__ inline size_t rows_warp_bytes(int S, int A) {
     const size_t ncell = (size_t)S * A;
-    size_t b = ncell * 3 * sizeof(double)      // s1, s2, val
-               + (size_t)S * 2 * sizeof(double) // smax, sub2
-               + ncell * sizeof(unsigned)       // cnt
-               + (size_t)S * 3 * sizeof(int)    // sarg, steps, actstep
-               + (size_t)A * sizeof(unsigned);  // per-warp histogram of chosen actions
+    size_t b = ncell * sizeof(Cell)               // s1, s2, val
+               + (size_t)S * 2 * sizeof(double)   // smax, sub2
+               + ncell * sizeof(unsigned)         // cnt
+               + (size_t)S * 3 * sizeof(int)      // sarg, actstep, flushpt
+               + (size_t)A * sizeof(unsigned);    // per-warp histogram of chosen actions
     return (b + 15) & ~(size_t)15;
 }
+constexpr size_t kRowsCtaFixedBytes = kLut * sizeof(double2);
 
 template <typename RT, typename OT, bool OVERALL>
-__global__ void __launch_bounds__(128) k_stream_rows(const StreamArgs p, const int warps_per_cta,
+__global__ void __launch_bounds__(256, 4) k_stream_rows(const StreamArgs p, const int warps_per_cta,
                                                       const unsigned warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
+
+    double2 *lut = reinterpret_cast<double2 *>(smem_raw);
+    for (int i = threadIdx.x; i < kLut; i += blockDim.x)
+        lut[i] = make_double2(i ? rsqrt_pos((double)i) : 0.0, rsqrt_pos((double)i + 1.0));
+    __syncthreads();   // the only block-wide barrier (before any warp may leave)
+
     const long long inst = (long long)blockIdx.x * warps_per_cta + warp;
-    if (inst >= p.n_inst) return;  // whole warp leaves; no block-wide barriers below
+    if (inst >= p.n_inst) return;
 
     const int S = p.S, A = p.A, ncell = S * A;
-    double *s1 = reinterpret_cast<double *>(smem_raw + (size_t)warp * warp_bytes);
-    double *s2 = s1 + ncell;
-    double *val = s2 + ncell;
-    double *smax = val + ncell;
+    Cell *cells = reinterpret_cast<Cell *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
+    double *smax = reinterpret_cast<double *>(cells + ncell);
     double *sub2 = smax + S;
     unsigned *cnt = reinterpret_cast<unsigned *>(sub2 + S);
     int *sarg = reinterpret_cast<int *>(cnt + ncell);
-    int *steps = sarg + S;
-    int *actstep = steps + S;
-    unsigned *hist = reinterpret_cast<unsigned *>(actstep + S);
+    int *actstep = sarg + S;
+    int *flushpt = actstep + S;
+    unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
 
     for (int c = lane; c < ncell; c += 32) {
-        s1[c] = 0.0; s2[c] = 0.0; cnt[c] = 0u;
-        val[c] = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
+        cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
+        cells[c].val = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
     }
     for (int a = lane; a < A; a += 32) hist[a] = 0u;
     __syncwarp();
     {
         double m0, sec0; int g0;
-        warp_top2(val, A, m0, g0, sec0);   // every state starts identical
+        warp_top2(&cells[0].val, 3, A, m0, g0, sec0);   // every state starts identical
         const double ub0 = runner_up_bound(sec0, m0);
         for (int s = lane; s < S; s += 32) {
-            smax[s] = m0; sub2[s] = ub0; sarg[s] = g0; steps[s] = 0; actstep[s] = -1;   // ST1:58
+            smax[s] = m0; sub2[s] = ub0; sarg[s] = g0; actstep[s] = -1; flushpt[s] = 0;   // ST1:58
         }
     }
     __syncwarp();
 
     const unsigned lt = lanemask_lt(), le = lanemask_le(), gt = lanemask_gt();
-    const long long row0 = inst * p.n_steps;
+    const unsigned n_steps = p.n_steps;
+    const long long row0 = inst * (long long)n_steps;
     const int *gidx = p.idx + row0;
     const int *gact = p.act + row0;
     const RT *gR = reinterpret_cast<const RT *>(p.R) + row0;
     OT *oval = reinterpret_cast<OT *>(p.out_value) + row0;
     int *oact = p.out_act + row0;
     OT *oall = OVERALL ? reinterpret_cast<OT *>(p.out_overall) + row0 : nullptr;
+    const double c_h = p.c_h, cap = p.cap, bonus = p.bonus;
+    const int rule = p.rule_act;
+    const unsigned n_thres = (unsigned)p.n_thres;
 
-    double total = 0.0;          // running overall_value (ST2:99-105), warp-uniform
-    unsigned long long bad = 0;  // lane-local count of out-of-range rows
+    double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
+    unsigned bad = 0;     // lane-local count of out-of-range rows
 
     // software prefetch: rows of batch b+1 are requested while batch b is processed
     int n_idx = 0, n_act = 0;
     RT n_R = RT(0);
-    if (lane < p.n_steps) { n_idx = ld_stream(gidx + lane); n_act = ld_stream(gact + lane); n_R = ld_stream(gR + lane); }
+    if ((unsigned)lane < n_steps) { n_idx = ld_stream(gidx + lane); n_act = ld_stream(gact + lane); n_R = ld_stream(gR + lane); }
 
-    for (long long k0 = 0; k0 < p.n_steps; k0 += 32) {
-        const long long k = k0 + lane;
-        const bool in_stream = k < p.n_steps;
-        const int s_in = n_idx, a_in = n_act;
+    for (unsigned k0 = 0; k0 < n_steps; k0 += 32) {
+        const unsigned k = k0 + lane;
+        const bool in_stream = k < n_steps;
+        const int s_in = n_idx, a = n_act;
         const double r = (double)n_R;
         {
-            const long long kn = k + 32;
-            if (kn < p.n_steps) { n_idx = ld_stream(gidx + kn); n_act = ld_stream(gact + kn); n_R = ld_stream(gR + kn); }
+            const unsigned kn = k + 32;
+            if (kn < n_steps) { n_idx = ld_stream(gidx + kn); n_act = ld_stream(gact + kn); n_R = ld_stream(gR + kn); }
         }
-        const bool active = in_stream && (unsigned)s_in < (unsigned)S && (unsigned)a_in < (unsigned)A;
+        const bool active = in_stream && (unsigned)s_in < (unsigned)S && (unsigned)a < (unsigned)A;
         if (in_stream && !active) bad++;
         // inactive lanes get a private key so they match nobody
         const int s = active ? s_in : (0x40000000 | lane);
-        const int a = a_in;
-        const int key = active ? s_in * A + a_in : (0x40000000 | lane);
+        const int key = active ? s_in * A + a : (0x40000000 | lane);
 
         // ---- phase 1: running moments of every row's cell, in time order -------------------
         const unsigned mk = __match_any_sync(FULL_MASK, key);
         const unsigned ms = __match_any_sync(FULL_MASK, s);
         unsigned n0 = 0;
         double acc1 = 0.0, acc2 = 0.0;
-        if (active) { n0 = cnt[key]; acc1 = s1[key]; acc2 = s2[key]; }
+        if (active) { n0 = cnt[key]; acc1 = cells[key].s1; acc2 = cells[key].s2; }
         unsigned earlier = mk & lt;
         while (__any_sync(FULL_MASK, earlier != 0)) {
             const int j = earlier ? (__ffs(earlier) - 1) : lane;
@@ -201,72 +249,105 @@ __global__ void __launch_bounds__(128) k_stream_rows(const StreamArgs p, const i
         acc2 = fma(r, r, acc2);
         const unsigned n = n0 + __popc(mk & lt) + 1u;
         __syncwarp();
-        if (active && (mk & gt) == 0) { cnt[key] = n; s1[key] = acc1; s2[key] = acc2; }
-        const bool upd = active && n > (unsigned)p.n_thres;                      // ST1:86
-        const double v = cell_value(n, acc1, acc2, a == p.rule_act, p.c_h, p.cap);
+        if (active && (mk & gt) == 0) { cnt[key] = n; cells[key].s1 = acc1; cells[key].s2 = acc2; }
+        const bool upd = active && n > n_thres;                                   // ST1:86
+        double v;
+        if (__all_sync(FULL_MASK, n < (unsigned)kLut)) {   // warp-uniform: no divergence around the table
+            const double2 rr = lut[n];
+            v = cell_value_rs(rr.x, rr.y, acc1, acc2, a == rule, c_h, cap);
+        } else {
+            v = cell_value(n, acc1, acc2, a == rule, c_h, cap);
+        }
 
         // ---- phase 2: per-row (max, argmax) of the row's state ----------------------------
-        unsigned pend = __ballot_sync(FULL_MASK, active);
-        bool mine = active;
-        double m_out = CUDART_NAN, smax0 = 0.0;
-        int g_out = -1;
-        bool first_round = true;
-        while (pend) {
-            double ms0 = 0.0, ub = 0.0;
-            int g = -1;
-            if (mine) { ms0 = smax[s]; g = sarg[s]; ub = sub2[s]; }
-            if (first_round) { smax0 = ms0; first_round = false; }
-            const bool T = mine && upd && a == g;        // row refreshes the argmax cell
+        double ms0 = 0.0, ub = 0.0;
+        int g = -1, ast = -1;
+        if (active) { ms0 = smax[s]; ub = sub2[s]; g = sarg[s]; ast = actstep[s]; }
+        const double smax0 = ms0;   // the state's max when the batch began (for overall_value)
+        double m_out;
+        int g_out = g;
+        {
+            // optimistic pass: nobody's argmax moves
+            const bool T = upd && a == g;   // row refreshes the argmax cell of its state
             const unsigned tm = __ballot_sync(FULL_MASK, T);
             const unsigned cand = tm & ms & le;
             const int jl = cand ? (31 - __clz(cand)) : lane;
             const double vj = shfl_f64(v, jl);
-            const double m_k = cand ? vj : ms0;
-            const bool fail = mine && upd && (T ? !(v > ub) : !(v <= ub && v < m_k));
-            const unsigned fm = __ballot_sync(FULL_MASK, fail);
-            const int j = fm ? (__ffs(fm) - 1) : 32;
-            const unsigned fin = fm ? (pend & ((1u << j) - 1u)) : pend;
-            if (mine && ((fin >> lane) & 1u)) {
-                g_out = g; m_out = m_k;
-                if (upd && (mk & fin & gt) == 0) val[key] = v;
-                if ((ms & fin & gt) == 0) smax[s] = m_k;
+            m_out = cand ? vj : ms0;
+            const bool fail = upd && (T ? !(v > ub) : !(v <= ub && v < m_out));
+            if (__ballot_sync(FULL_MASK, fail) == 0) {
+                if (upd && (mk & gt) == 0) cells[key].val = v;
+                if (active && (ms & gt) == 0) smax[s] = m_out;
+            } else {
+                // ---- general path: finalize rows up to the first doubtful one, replay it exactly,
+                //      retry the rest (nothing was written by the optimistic pass) -------------------
+                unsigned pend = __ballot_sync(FULL_MASK, active);
+                bool mine = active;
+                while (pend) {
+                    double c_ms0 = 0.0, c_ub = 0.0;
+                    int c_g = -1;
+                    if (mine) { c_ms0 = smax[s]; c_g = sarg[s]; c_ub = sub2[s]; }
+                    const bool cT = mine && upd && a == c_g;
+                    const unsigned ctm = __ballot_sync(FULL_MASK, cT);
+                    const unsigned ccand = ctm & ms & le;
+                    const int cjl = ccand ? (31 - __clz(ccand)) : lane;
+                    const double cvj = shfl_f64(v, cjl);
+                    const double m_k = ccand ? cvj : c_ms0;
+                    const bool cfail = mine && upd && (cT ? !(v > c_ub) : !(v <= c_ub && v < m_k));
+                    const unsigned fm = __ballot_sync(FULL_MASK, cfail);
+                    const int j = fm ? (__ffs(fm) - 1) : 32;
+                    const unsigned fin = fm ? (pend & ((1u << j) - 1u)) : pend;
+                    if (mine && ((fin >> lane) & 1u)) {
+                        g_out = c_g; m_out = m_k;
+                        if (upd && (mk & fin & gt) == 0) cells[key].val = v;
+                        if ((ms & fin & gt) == 0) smax[s] = m_k;
+                    }
+                    if (fm == 0) break;
+                    __syncwarp();
+                    const int sj = __shfl_sync(FULL_MASK, s, j);
+                    const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
+                    if (lane == j) cells[key].val = v;
+                    __syncwarp();
+                    const int old_g = sarg[sj];
+                    double mx, second; int arg;
+                    warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
+                    if (arg != old_g) {
+                        // rows (flushpt, t_j) of this state were emitted with old_g: account for them
+                        unsigned csum = 0;
+                        for (int q = lane; q < A; q += 32) csum += cnt[sj * A + q];
+                        const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
+                        if (lane == j) { hist[old_g] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1; }
+                    }
+                    if (lane == j) {
+                        g_out = arg; m_out = mx;
+                        smax[sj] = mx; sarg[sj] = arg; sub2[sj] = runner_up_bound(second, mx);
+                    }
+                    __syncwarp();
+                    pend &= ~(fin | (1u << j));
+                    mine = mine && lane > j;
+                }
             }
-            if (fm == 0) break;
-            __syncwarp();
-            // exact replay of row j: apply its update, rescan its state
-            const int sj = __shfl_sync(FULL_MASK, s, j);
-            if (lane == j) val[key] = v;
-            __syncwarp();
-            double mx, second; int arg;
-            warp_top2(val + sj * A, A, mx, arg, second);
-            if (lane == j) {
-                g_out = arg; m_out = mx;
-                smax[sj] = mx; sarg[sj] = arg; sub2[sj] = runner_up_bound(second, mx);
-            }
-            __syncwarp();
-            pend &= ~(fin | (1u << j));
-            mine = mine && lane > j;
         }
-        __syncwarp();
 
-        // ---- activation step (ST1:98-99) and overall_value (ST2:99-105) -------------------
-        int t_before = 0, ast = -1;
-        if (active) { t_before = steps[s]; ast = actstep[s]; }
-        const unsigned nonrule = __ballot_sync(FULL_MASK, active && g_out != p.rule_act) & ms;
-        const bool act_before = ast != -1;
-        const int rank_s = __popc(ms & lt);
-        __syncwarp();
-        if (active) {
-            if (!act_before && nonrule && lane == __ffs(nonrule) - 1) actstep[s] = t_before + rank_s + 1;
-            if ((ms & gt) == 0) steps[s] = t_before + __popc(ms);
+        // ---- activation step (ST1:98-99): first row of a state whose argmax is not the rule action
+        const unsigned need = __ballot_sync(FULL_MASK, active && ast == -1 && g_out != rule) & ms;
+        if (__any_sync(FULL_MASK, need != 0)) {   // rare: once per state
+            __syncwarp();
+            if (need && lane == __ffs(need) - 1) {
+                unsigned csum = 0;
+                for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
+                actstep[s] = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
+            }
+            __syncwarp();
         }
-        if (OVERALL) {
-            const bool act_now = act_before || (nonrule & le) != 0;
-            const double c_k = (active && act_now) ? m_out + p.bonus : 0.0;
+        if (OVERALL) {                                                            // ST2:99-105
+            const bool act_before = ast != -1;
+            const bool act_now = act_before || (need & le) != 0;
+            const double c_k = (active && act_now) ? m_out + bonus : 0.0;
             const unsigned prev = ms & lt;
             const int pl = prev ? (31 - __clz(prev)) : lane;
             const double c_prev_lane = shfl_f64(c_k, pl);
-            const double c_prev = prev ? c_prev_lane : (act_before ? smax0 + p.bonus : 0.0);
+            const double c_prev = prev ? c_prev_lane : (act_before ? smax0 + bonus : 0.0);
             double d = active ? c_k - c_prev : 0.0;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -278,22 +359,24 @@ __global__ void __launch_bounds__(128) k_stream_rows(const StreamArgs p, const i
             if (in_stream) st_stream(oall + k, (OT)ov);
         }
         if (in_stream) {
-            st_stream(oval + k, (OT)m_out);
+            st_stream(oval + k, active ? (OT)m_out : (OT)CUDART_NAN);
             st_stream(oact + k, g_out);
         }
-        if (p.act_hist != nullptr) {
-            const int hk = active ? g_out : (0x40000000 | lane);
-            const unsigned mh = __match_any_sync(FULL_MASK, hk);
-            if (active && (mh & lt) == 0) hist[g_out] += __popc(mh);
-            __syncwarp();
-        }
+        __syncwarp();   // table writes of this batch are ordered before the next batch's reads
     }
-    __syncwarp();
     for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)actstep[s];
-    if (p.act_hist != nullptr)
+    if (p.act_hist != nullptr) {
+        // rows since the last argmax change of each state carry the state's current argmax
+        for (int s = lane; s < S; s += 32) {
+            unsigned csum = 0;
+            for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
+            atomicAdd(&hist[sarg[s]], csum - (unsigned)flushpt[s]);
+        }
+        __syncwarp();
         for (int a = lane; a < A; a += 32)
             if (hist[a]) atomicAdd(p.act_hist + a, (unsigned long long)hist[a]);
-    if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, bad);
+    }
+    if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, (unsigned long long)bad);
 }
 
 // ---- general-shape walker: tables in global memory, one row at a time ----------------------
@@ -326,25 +409,26 @@ __global__ void __launch_bounds__(128) k_stream_walk(const StreamArgs p, unsigne
     __syncwarp();
     {
         double m0, sec0; int g0;
-        warp_top2(val, A, m0, g0, sec0);
+        warp_top2(val, 1, A, m0, g0, sec0);
         for (int s = lane; s < S; s += 32) { smax[s] = m0; steps[s] = 0; actstep[s] = -1; }
     }
     __syncwarp();
 
-    const long long row0 = inst * p.n_steps;
+    const long long n_steps = p.n_steps;
+    const long long row0 = inst * n_steps;
     const RT *gR = reinterpret_cast<const RT *>(p.R) + row0;
     OT *oval = reinterpret_cast<OT *>(p.out_value) + row0;
     OT *oall = OVERALL ? reinterpret_cast<OT *>(p.out_overall) + row0 : nullptr;
     unsigned long long bad = 0;
 
-    for (long long k0 = 0; k0 < p.n_steps; k0 += 32) {
+    for (long long k0 = 0; k0 < n_steps; k0 += 32) {
         const long long k = k0 + lane;
         int b_idx = 0, b_act = 0;
         double b_r = 0.0;
-        if (k < p.n_steps) { b_idx = p.idx[row0 + k]; b_act = p.act[row0 + k]; b_r = (double)gR[k]; }
+        if (k < n_steps) { b_idx = p.idx[row0 + k]; b_act = p.act[row0 + k]; b_r = (double)gR[k]; }
         double o_val = CUDART_NAN, o_all = 0.0;
         int o_act = -1;
-        const int nrow = (int)min((long long)32, p.n_steps - k0);
+        const int nrow = (int)min((long long)32, n_steps - k0);
         for (int t = 0; t < nrow; ++t) {
             const int s = __shfl_sync(FULL_MASK, b_idx, t);
             const int a = __shfl_sync(FULL_MASK, b_act, t);
@@ -363,7 +447,7 @@ __global__ void __launch_bounds__(128) k_stream_walk(const StreamArgs p, unsigne
                 }
                 __syncwarp();
                 double second;
-                warp_top2(val + s * A, A, mx, arg, second);
+                warp_top2(val + s * A, 1, A, mx, arg, second);
                 if (lane == 0) {
                     smax[s] = mx;
                     const int st = steps[s] + 1;
@@ -386,7 +470,7 @@ __global__ void __launch_bounds__(128) k_stream_walk(const StreamArgs p, unsigne
             }
             if (lane == t) { o_val = mx; o_act = arg; o_all = ov; }
         }
-        if (k < p.n_steps) {
+        if (k < n_steps) {
             oval[k] = (OT)o_val;
             p.out_act[row0 + k] = o_act;
             if (OVERALL) oall[k] = (OT)o_all;
@@ -398,50 +482,97 @@ __global__ void __launch_bounds__(128) k_stream_walk(const StreamArgs p, unsigne
     if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, bad);
 }
 
-// ---- summary statistics (fixed-order float64 reduction) -------------------------------------
+// ---- summary statistics (fixed-order float64 reduction, one CTA) -----------------------------
 template <typename OT>
-__global__ void __launch_bounds__(256) k_stream_stats(const OT *out_value, const OT *out_overall,
-                                                       const long long *activation,
-                                                       const unsigned long long *act_hist,
-                                                       long long n_inst, long long n_steps, int S, int A,
-                                                       double *stats) {
-    __shared__ double sh[4][256];
+__global__ void __launch_bounds__(1024) k_stream_stats(const OT *__restrict__ out_value,
+                                                        const OT *__restrict__ out_overall,
+                                                        const long long *__restrict__ activation,
+                                                        const unsigned long long *__restrict__ act_hist,
+                                                        long long n_inst, long long n_steps, int S, int A,
+                                                        double *__restrict__ stats) {
+    __shared__ double sh[4][1024];
     const int t = threadIdx.x;
     double v = 0.0, o = 0.0, na = 0.0, sa = 0.0;
-    if (n_steps > 0)
-        for (long long i = t; i < n_inst; i += 256) {
-            v += (double)out_value[i * n_steps + n_steps - 1];
-            if (out_overall) o += (double)out_overall[i * n_steps + n_steps - 1];
+    if (n_steps > 0) {
+        const OT *lv = out_value + n_steps - 1;
+        const OT *lo = out_overall ? out_overall + n_steps - 1 : nullptr;
+        for (long long i = t; i < n_inst; i += 4096) {   // four independent loads in flight per array
+            OT x[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long ii = i + 1024ll * u;
+                x[u] = ii < n_inst ? lv[ii * n_steps] : OT(0);
+                y[u] = (lo && ii < n_inst) ? lo[ii * n_steps] : OT(0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { v += (double)x[u]; o += (double)y[u]; }
         }
-    for (long long i = t; i < n_inst * S; i += 256) {
-        const long long st = activation[i];
-        if (st != -1) { na += 1.0; sa += (double)st; }
+    }
+    const long long n_as = n_inst * S;
+    for (long long i = t; i < n_as; i += 8192) {
+        long long st[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const long long ii = i + 1024ll * u; st[u] = ii < n_as ? activation[ii] : -1; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (st[u] != -1) { na += 1.0; sa += (double)st[u]; }
     }
     sh[0][t] = v; sh[1][t] = o; sh[2][t] = na; sh[3][t] = sa;
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
+    for (int w = 512; w > 0; w >>= 1) {
         if (t < w)
             for (int q = 0; q < 4; ++q) sh[q][t] += sh[q][t + w];
         __syncthreads();
     }
     if (t < 4) stats[t] = sh[t][0];
     if (t == 4) stats[4] = (double)n_inst * (double)n_steps;
-    for (int a = t; a < A; a += 256) stats[DCARL_STATS_HEADER + a] = act_hist ? (double)act_hist[a] : 0.0;
+    for (int a = t; a < A; a += 1024) stats[DCARL_STATS_HEADER + a] = act_hist ? (double)act_hist[a] : 0.0;
+}
+
+// ---- the closed form on caller-held moments (also the precision probe of cell_value) ---------
+__global__ void __launch_bounds__(256) k_cell_values(const int *__restrict__ n, const double *__restrict__ s1,
+                                                      const double *__restrict__ s2,
+                                                      const int *__restrict__ act, long long count, double c_h,
+                                                      double cap, int rule_act, double *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[i] = n[i] > 0 ? cell_value((unsigned)n[i], s1[i], s2[i], act[i] == rule_act, c_h, cap) : CUDART_NAN;
 }
 
 // ---- host side -------------------------------------------------------------------------------
-static const size_t kMaxSmem = 227 * 1024;
+static const size_t kMaxSmemPerCta = 227 * 1024;
+static const size_t kSmemPerSm = 228 * 1024;
+
+// warps (= instances) per CTA: minimise the work of the busiest SM, then prefer larger CTAs
+static int pick_warps_per_cta(long long n_inst, size_t wb, int sms) {
+    int best = 1;
+    long long best_cost = -1;
+    for (int w = 1; w <= 8; ++w) {
+        const size_t cta = kRowsCtaFixedBytes + wb * w;
+        if (cta > kMaxSmemPerCta) break;
+        long long resident = (long long)(kSmemPerSm / (cta + 1024)) * w;   // warps per SM that fit
+        if (resident > 32) resident = 32;                                   // 64 registers per thread
+        const long long ctas = (n_inst + w - 1) / w;
+        const long long per_sm = (ctas + sms - 1) / sms * w;                // warps the busiest SM runs
+        const long long rounds = (per_sm + resident - 1) / resident;
+        const long long cost = rounds * resident * 1000 + per_sm;          // full rounds dominate
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = w; }
+    }
+    return best;
+}
 
 template <typename RT, typename OT, bool OV>
 static int launch_rows(const StreamArgs &a, cudaStream_t st) {
     const size_t wb = rows_warp_bytes(a.S, a.A);
-    int wpc = (int)(kMaxSmem / wb);
-    if (wpc < 1) return -1;
-    if (wpc > 4) wpc = 4;
-    const size_t smem = wb * wpc;
+    const int wpc = pick_warps_per_cta(a.n_inst, wb, sm_count());
+    const size_t smem = kRowsCtaFixedBytes + wb * wpc;
     auto kern = k_stream_rows<RT, OT, OV>;
-    DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    static size_t configured = 0;   // per template instance; growing only
+    if (smem > configured) {
+        DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
+        DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = kMaxSmemPerCta;
+    }
     const long long grid = (a.n_inst + wpc - 1) / wpc;
     kern<<<(unsigned)grid, wpc * 32, smem, st>>>(a, wpc, (unsigned)wb);
     DCARL_LAUNCH_CHECK("k_stream_rows");
@@ -489,7 +620,7 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     if (!(p->alpha > 0.0 && p->alpha <= 1.0)) return bad_arg(9, "alpha must be in (0, 1]");
     if (p->rule_act < 0 || p->rule_act >= A) return bad_arg(9, "rule_act outside [0, A)");
     if (p->n_thres < 0) return bad_arg(9, "n_thres < 0");
-    if (n_steps > 0xfffffff0ll) return bad_arg(6, "n_steps does not fit the 32-bit cell counters");
+    if (n_steps > 0x7fffffc0ll) return bad_arg(6, "n_steps does not fit the 32-bit row counters");
     if (n_inst == 0) return 0;
     if (!out_activation_step) return bad_arg(13, "out_activation_step is null");
     if (n_steps > 0 && (!idx || !act || !R)) return bad_arg(1, "idx/act/R is null");
@@ -497,7 +628,7 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     if (variant < 0 || variant > 2) return bad_arg(19, "variant must be 0, 1 or 2");
     if ((n_inst + 3) / 4 > 0x7fffffffll) return bad_arg(5, "n_inst too large for one launch");
 
-    const bool fits = rows_warp_bytes(S, A) <= kMaxSmem;
+    const bool fits = kRowsCtaFixedBytes + rows_warp_bytes(S, A) <= kMaxSmemPerCta;
     bool rows = fits;
     if (variant == 1) rows = false;
     if (variant == 2 && !fits) return bad_arg(19, "the S*A table does not fit shared memory");
@@ -512,7 +643,7 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     a.out_overall = out_overall;
     a.act_hist = reinterpret_cast<unsigned long long *>(act_hist);
     a.bad_rows = reinterpret_cast<unsigned long long *>(bad_rows);
-    a.n_inst = n_inst; a.n_steps = n_steps; a.S = S; a.A = A;
+    a.n_inst = n_inst; a.n_steps = (unsigned)n_steps; a.S = S; a.A = A;
     a.c_h = p->scale * sqrt(log(1.0 / p->alpha) / 2.0);
     a.cap = p->cap; a.prior_rule = p->prior_rule; a.prior_other = p->prior_other;
     a.bonus = p->activation_bonus; a.n_thres = p->n_thres; a.rule_act = p->rule_act;
@@ -520,6 +651,21 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     if (r_is_f64)
         return out_is_f64 ? dispatch_ov<double, double>(a, rows, ws, st) : dispatch_ov<double, float>(a, rows, ws, st);
     return out_is_f64 ? dispatch_ov<float, double>(a, rows, ws, st) : dispatch_ov<float, float>(a, rows, ws, st);
+}
+
+extern "C" int dcarl_cell_values(const int32_t *n, const double *sum, const double *sumsq, const int32_t *act,
+                                 int64_t count, const dcarl_params *p, double *out, dcarl_stream_t stream) {
+    if (count < 0) return bad_arg(5, "count < 0");
+    if (!p) return bad_arg(6, "params is null");
+    if (!(p->alpha > 0.0 && p->alpha <= 1.0)) return bad_arg(6, "alpha must be in (0, 1]");
+    if (count == 0) return 0;
+    if (!n || !sum || !sumsq || !act) return bad_arg(1, "null input");
+    if (!out) return bad_arg(7, "out is null");
+    const double c_h = p->scale * sqrt(log(1.0 / p->alpha) / 2.0);
+    k_cell_values<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, sum, sumsq, act, count, c_h,
+                                                                                     p->cap, p->rule_act, out);
+    DCARL_LAUNCH_CHECK("k_cell_values");
+    return 0;
 }
 
 extern "C" int dcarl_stream_stats(const void *out_value, int out_is_f64, const void *out_overall,
@@ -535,11 +681,11 @@ extern "C" int dcarl_stream_stats(const void *out_value, int out_is_f64, const v
     const long long *as = reinterpret_cast<const long long *>(out_activation_step);
     const unsigned long long *ah = reinterpret_cast<const unsigned long long *>(act_hist);
     if (out_is_f64)
-        k_stream_stats<double><<<1, 256, 0, st>>>((const double *)out_value, (const double *)out_overall, as, ah,
-                                                  n_inst, n_steps, S, A, stats);
+        k_stream_stats<double><<<1, 1024, 0, st>>>((const double *)out_value, (const double *)out_overall, as, ah,
+                                                   n_inst, n_steps, S, A, stats);
     else
-        k_stream_stats<float><<<1, 256, 0, st>>>((const float *)out_value, (const float *)out_overall, as, ah,
-                                                 n_inst, n_steps, S, A, stats);
+        k_stream_stats<float><<<1, 1024, 0, st>>>((const float *)out_value, (const float *)out_overall, as, ah,
+                                                  n_inst, n_steps, S, A, stats);
     DCARL_LAUNCH_CHECK("k_stream_stats");
     return 0;
 }

@@ -8,6 +8,8 @@ CUDA tensors in -> CUDA tensors out (no copies, asynchronous on the current stre
 from dataclasses import dataclass
 from typing import Optional
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -51,6 +53,7 @@ class StreamPlan:
         self.ws = e((max(need, 16),), torch.uint8)
         self._ws_bytes = need
         self._pinned = None
+        self._streams = None
 
     # -- device path -------------------------------------------------------------------------
     def run_device(self, idx, act, R, stream=None, check=False):
@@ -104,21 +107,67 @@ class StreamPlan:
         w = 8 if self.out_dtype == torch.float64 else 4
         return self.n_inst * self.n_steps * (4 + w * (2 if self.want_overall else 1)) + self.n_inst * self.S * 8
 
-    def run_pinned(self, stream=None):
-        """Inputs already in the plan's pinned host buffers (``plan.pinned()['idx'|'act'|'R']``):
-        H2D, kernel, D2H of every output on one stream; returns after the stream has drained."""
+    def _launch_range(self, lo, hi, stream):
+        """Kernel launch for instances [lo, hi) of the plan's own input/output buffers."""
+        ns = self.n_steps
+        rb = 8 if self.r_dtype == torch.float64 else 4
+        ob = 8 if self.out_dtype == torch.float64 else 4
+        di, da, dr = self._din
+        off = lambda t, w: C.c_void_p(t.data_ptr() + lo * ns * w) if t is not None else None
+        _abi.check(_abi.lib().dcarl_stream_bounds(
+            off(di, 4), off(da, 4), off(dr, rb), int(self.r_dtype == torch.float64),
+            hi - lo, ns, self.S, self.A, self.params,
+            off(self.value, ob), int(self.out_dtype == torch.float64), off(self.act, 4),
+            C.c_void_p(self.activation_step.data_ptr() + lo * self.S * 8), off(self.overall, ob),
+            _dev.ptr(self.act_hist), _dev.ptr(self.bad_rows),
+            C.c_void_p(self.ws.data_ptr() + (lo * (self._ws_bytes // max(self.n_inst, 1)))), self._ws_bytes,
+            self.variant, _dev.stream_handle(stream)))
+
+    def run_pinned(self, chunks=4):
+        """Inputs already in the plan's pinned host buffers (``plan.pinned()['idx'|'act'|'R']``).
+        Instances are cut into `chunks` pieces that flow through three streams — host->device copy,
+        kernel, device->host copy — so the two PCIe directions and the kernel overlap.  Returns the
+        pinned buffers after everything has drained."""
         pin = self._pin()
-        st = stream or torch.cuda.current_stream()
-        with torch.cuda.stream(st):
-            for d, h in zip(self._din, (pin["idx"], pin["act"], pin["R"])):
-                d.copy_(h, non_blocking=True)
-            self.run_device(*self._din, stream=st)
-            pin["value"].copy_(self.value, non_blocking=True)
-            pin["oact"].copy_(self.act, non_blocking=True)
-            if self.want_overall:
-                pin["overall"].copy_(self.overall, non_blocking=True)
-            pin["astep"].copy_(self.activation_step, non_blocking=True)
-        st.synchronize()
+        if self._streams is None:
+            self._streams = tuple(torch.cuda.Stream(device=self.device) for _ in range(3))
+        s_in, s_k, s_out = self._streams
+        cur = torch.cuda.current_stream()
+        for st in self._streams:
+            st.wait_stream(cur)
+        chunks = max(1, min(int(chunks), self.n_inst))
+        edges = [self.n_inst * c // chunks for c in range(chunks + 1)]
+        with torch.cuda.stream(s_k):
+            if self.want_stats:
+                self.act_hist.zero_()
+            self.bad_rows.zero_()
+        outs = [(pin["value"], self.value), (pin["oact"], self.act), (pin["astep"], self.activation_step)]
+        if self.want_overall:
+            outs.append((pin["overall"], self.overall))
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            if hi == lo:
+                continue
+            with torch.cuda.stream(s_in):
+                for d, h in zip(self._din, (pin["idx"], pin["act"], pin["R"])):
+                    d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            s_k.wait_event(ev_in)
+            self._launch_range(lo, hi, s_k)
+            ev_k = torch.cuda.Event()
+            ev_k.record(s_k)
+            s_out.wait_event(ev_k)
+            with torch.cuda.stream(s_out):
+                for h, d in outs:
+                    h[lo:hi].copy_(d[lo:hi], non_blocking=True)
+        if self.want_stats:
+            _abi.check(_abi.lib().dcarl_stream_stats(
+                _dev.ptr(self.value), int(self.out_dtype == torch.float64), _dev.ptr(self.overall),
+                _dev.ptr(self.activation_step), _dev.ptr(self.act_hist), self.n_inst, self.n_steps,
+                self.S, self.A, _dev.ptr(self.stats), _dev.stream_handle(s_k)))
+        for st in self._streams:
+            cur.wait_stream(st)
+        cur.synchronize()
         return pin
 
     def pinned(self):

@@ -98,6 +98,14 @@ int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const void *R, i
                         uint64_t *act_hist, uint64_t *bad_rows,
                         void *ws, size_t ws_bytes, int variant, dcarl_stream_t stream);
 
+/* The bound of a cell from caller-held moments, exactly as the stream kernel evaluates it:
+ * cell i holds n[i] > 0 samples with sum[i] and sumsq[i]; act[i] == rule_act selects the upper
+ * bound (ST1:12), anything else min(lower, CI lower) (ST1:16, 24).  out[i] float64; NaN for n <= 0.
+ * (n_thres is not applied here: the caller decides whether the cell refreshes, ST1:86.) */
+int dcarl_cell_values(const int32_t *n, const double *sum, const double *sumsq, const int32_t *act,
+                      int64_t count, const dcarl_params *p /* host */, double *out,
+                      dcarl_stream_t stream);
+
 /* Summary statistics of one batch, the vector that is all-reduced across GPUs:
  * stats[0] = sum_i out_value[i, n_steps-1]       stats[1] = sum_i out_overall[i, n_steps-1] (0 if null)
  * stats[2] = # activated (instance,state) pairs  stats[3] = sum of their activation_step

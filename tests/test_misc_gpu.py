@@ -38,6 +38,40 @@ def test_bound_functions_golden(golden):
     assert np.abs(o[0].cpu().numpy() - np.array(w)).max() < 1e-9
 
 
+def test_cell_value_closed_form_is_accurate_to_a_few_ulp():
+    """The rsqrt-based closed form of the stream kernel against the reference's divide/sqrt chain
+    (test_DCARL.py:12,16,24) in float64: this bounds how close a tie must be to flip an argmax."""
+    import math
+    rng = np.random.default_rng(1)
+    m = 200000
+    n = np.concatenate([rng.integers(1, 300, m // 2), rng.integers(300, 2_000_000, m // 2)]).astype(np.int64)
+    mean = rng.uniform(-200, 200, m)
+    sd = rng.uniform(0, 80, m) * (rng.random(m) > 0.05)
+    s1 = mean * n
+    s2 = (sd ** 2 + (s1 / n) ** 2) * n
+    act = rng.integers(0, 3, m).astype(np.int32)
+    got = dc.cell_values(n, s1, s2, act)
+    L = math.log(1 / 0.05)
+    mu = s1 / n
+    var = np.maximum(s2 / n - mu * mu, 0.0)
+    ub = np.minimum(100.0, mu + 150 * np.sqrt(L / 2 / n))
+    lb = mu - 150 * np.sqrt(L / 2 / n)
+    ci = s1 / n / (n + 1) - 4 * np.sqrt(var) / (n + 1) + s1 / (n + 1) - 150 * np.sqrt(L / 2 / (n + 1))
+    want = np.where(act == 0, ub, np.minimum(lb, ci))
+    # sigma = sqrt(s2/n - mean^2) carries that subtraction's cancellation error on BOTH sides
+    # (eps*(mean^2+var), divided by 2*sigma, times 4/(n+1)); everything else is a few ulp
+    eps = 2.2e-16
+    sig = np.sqrt(var)
+    tol = 2e-13 * np.maximum(1.0, np.abs(want))
+    nz = (act != 0) & (sig > 0)
+    tol[nz] += 32 * eps * (mu[nz] ** 2 + var[nz]) / sig[nz] / (n[nz] + 1)
+    tol[(act != 0) & (sig == 0)] += 1e-5
+    err = np.abs(got - want)
+    assert (err <= tol).all(), (err / tol).max()
+    assert (err[act == 0] <= 2e-13 * np.maximum(1.0, np.abs(want[act == 0]))).all()
+    assert np.isnan(dc.cell_values([0], [1.0], [1.0], [0]))[0]
+
+
 def test_data_generation_reproduces_the_reference_files(golden, tmp_path):
     """Seed numpy / random like tools/make_golden.py did before calling the reference's
     Data_Generation(): the three .npy files must come out bit-identical."""
