@@ -299,11 +299,89 @@ def run_ours(args):
         }
     if rank == 0 and world == 1 and not args.no_cpu:
         out.update(cpu_legs(plan, idx, act, R))
+    if rank == 0 and world == 1 and not args.no_secondary:
+        del idx, act, R
+        plan = None
+        torch.cuda.empty_cache()
+        try:
+            out["secondary"] = secondary(dev, measured_peak()[0])
+        except Exception as e:   # noqa: BLE001  (secondary numbers must never cost the headline line)
+            out["secondary"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as tdist
         tdist.destroy_process_group()
+
+
+def secondary(dev, peak):
+    """Roofline of the other kernels on the path (BASELINE configs 3 and 4, single-GPU share):
+    CUDA-event time of back-to-back launches on inputs larger than L2."""
+    import torch
+    import dcarl_b200 as dc
+    out = {}
+
+    def timed(fn, reps):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # config 4 (one GPU's view): 1e7-row buffer, 256 candidate actions, Q = 1 and Q = 64
+    g = torch.Generator(device=dev).manual_seed(3000)
+    M, NA = 10_000_000, 256
+    dist = torch.tensor(dc.VISITED_STATE_DIST[0], dtype=torch.float64, device=dev)
+    centers = torch.randn((4096, 20), generator=g, device=dev) * dist[:20].float()
+    buf = dc.BoxBuffer(20, capacity=M)
+    st = centers[torch.randint(0, 4096, (M,), generator=g, device=dev)]
+    st += torch.randn((M, 20), generator=g, device=dev) * (0.25 * dist[:20].float())
+    a = torch.randint(0, NA, (M, 1), generator=g, device=dev).float()
+    ret = -(0.95 ** torch.randint(0, 10, (M,), generator=g, device=dev).float()) * (torch.rand(M, generator=g, device=dev) < 0.5)
+    buf.append(torch.cat([st, a], 1), ret)
+    del st, a, ret
+    for Q in (1, 64):
+        q = centers[:Q].double().contiguous()
+        mom = torch.empty((Q, NA, 3), dtype=torch.float64, device=dev)
+        ms = timed(lambda: buf.moments(q, NA, out=mom), 20)
+        gbs = M * 88 / (ms * 1e-3) / 1e9
+        out[f"box_moments_Q{Q}"] = {"rows": M, "n_actions": NA, "ms": ms, "rows_per_s": M / (ms * 1e-3),
+                                    "queries_per_s": Q / (ms * 1e-3), "achieved_GBs": gbs, "frac": gbs / peak,
+                                    "algorithmic_bytes_per_row": 88, "matched_rows": float(mom[:, :, 0].sum())}
+    del buf
+    # config 3 mode A: 65 536 episodes x 200 draws, deviates supplied (16 B/row) and on-device Philox (12 B/row)
+    n = 65536 * 200
+    qs = torch.rand((20, 11), generator=g, device=dev) * 150 - 50
+    zs, zr = torch.randn(n, generator=g, device=dev), torch.randn(n, generator=g, device=dev)
+    ac = torch.randint(0, 11, (n,), generator=g, device=dev, dtype=torch.int32)
+    ms = timed(lambda: dc.sample_returns(qs, zs, ac, zr), 50)
+    out["sample_returns"] = {"rows": n, "ms": ms, "rows_per_s": n / (ms * 1e-3), "achieved_GBs": n * 20 / (ms * 1e-3) / 1e9,
+                             "frac": n * 20 / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_row": 20,
+                             "note": "12 B read (z_state, z_ret, act) + 8 B written (idx, R); includes two torch.empty per call"}
+    ms = timed(lambda: dc.sample_returns_philox(qs, n, 7), 50)
+    out["sample_returns_philox"] = {"rows": n, "ms": ms, "rows_per_s": n / (ms * 1e-3),
+                                    "achieved_GBs": n * 12 / (ms * 1e-3) / 1e9, "frac": n * 12 / (ms * 1e-3) / 1e9 / peak,
+                                    "algorithmic_bytes_per_row": 12}
+    # config 3 mode B: constant-velocity rollout surrogate, 65 536 episodes x 200 steps (not bandwidth bound)
+    ne = 65536
+    s0 = torch.zeros((ne, 20), device=dev)
+    s0[:, 2] = torch.rand(ne, generator=g, device=dev) * 6 + 2
+    for j in range(3):
+        b = 5 + 5 * j
+        s0[:, b] = torch.rand(ne, generator=g, device=dev) * 60 - 30
+        s0[:, b + 1] = torch.rand(ne, generator=g, device=dev) * 12 - 6
+        s0[:, b + 2] = torch.rand(ne, generator=g, device=dev) * 10 - 5
+        s0[:, b + 3] = torch.rand(ne, generator=g, device=dev) * 2 - 1
+    ra = torch.randint(0, 11, (ne,), generator=g, device=dev, dtype=torch.int32)
+    ms = timed(lambda: dc.rollout_cv(s0, ra), 50)
+    _, steps_run, _ = dc.rollout_cv(s0, ra)
+    out["rollout_cv"] = {"episodes": ne, "ms": ms, "kinematic_steps_per_s": float(steps_run.sum()) / (ms * 1e-3),
+                         "episodes_per_s": ne / (ms * 1e-3), "note": "96 B per episode: latency/compute bound, no roofline fraction"}
+    return out
 
 
 def cpu_legs(plan, idx, act, R):
@@ -375,6 +453,7 @@ def main():
     ap.add_argument("--n-inst", type=int, default=N_INST, help="instances per GPU (default: config 2)")
     ap.add_argument("--n-steps", type=int, default=N_STEPS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the box / sampler / rollout rooflines")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 3 if args.impl == "reference" else 50

@@ -144,42 +144,64 @@ __device__ __forceinline__ void warp_top2(const double *row, int stride, int A, 
 struct Cell {
     double s1, s2, val;
 };
+// per-state record: one 16-byte and one 8-byte shared load fetch everything a row needs
+struct __align__(16) StateRec {
+    double smax;   // current max_a value[s][a]
+    double sub2;   // runner-up bound: second-best <= sub2 < smax (== smax on an exact tie)
+    int sarg;      // current first argmax
+    int actstep;   // activation step, -1 = not yet (ST1:58)
+    int flushpt;   // rows of this state already counted in the action histogram
+    int pad;
+};
+// table entry for n < kLut: {1/n, c_h/sqrt(n), 1/(n+1), c_h/sqrt(n+1)}
+struct __align__(16) LutRec {
+    double inv_n, hn, inv_n1, hn1;
+};
 
 __host__ __device__ inline size_t rows_warp_bytes(int S, int A) {
     const size_t ncell = (size_t)S * A;
-    size_t b = ncell * sizeof(Cell)               // s1, s2, val
-               + (size_t)S * 2 * sizeof(double)   // smax, sub2
-               + ncell * sizeof(unsigned)         // cnt
-               + (size_t)S * 3 * sizeof(int)      // sarg, actstep, flushpt
-               + (size_t)A * sizeof(unsigned);    // per-warp histogram of chosen actions
+    size_t b = (size_t)S * sizeof(StateRec) + ncell * sizeof(Cell) + ncell * sizeof(unsigned) +
+               (size_t)A * sizeof(unsigned);   // states, cells, cnt, per-warp action histogram
     return (b + 15) & ~(size_t)15;
 }
-constexpr size_t kRowsCtaFixedBytes = kLut * sizeof(double2);
+constexpr size_t kRowsCtaFixedBytes = kLut * sizeof(LutRec);
+constexpr int kRowsMaxWarps = 7;
+
+// closed form with the table entries (see cell_value_rs)
+__device__ __forceinline__ double cell_value_lut(const LutRec &t, double s1, double s2, bool is_rule, double cap) {
+    const double mean = s1 * t.inv_n;
+    const double ub = dmin(cap, mean + t.hn);
+    const double var = fma(s2, t.inv_n, -mean * mean);
+    const double sigma = var > 1e-280 ? var * rsqrt_pos(var) : 0.0;
+    const double lb = mean - t.hn;
+    const double ci = fma(fma(-4.0, sigma, mean) + s1, t.inv_n1, -t.hn1);
+    return is_rule ? ub : dmin(lb, ci);
+}
 
 template <typename RT, typename OT, bool OVERALL>
-__global__ void __launch_bounds__(256, 4) k_stream_rows(const StreamArgs p, const int warps_per_cta,
-                                                      const unsigned warp_bytes) {
+__global__ void __launch_bounds__(kRowsMaxWarps * 32, 4)
+k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
 
-    double2 *lut = reinterpret_cast<double2 *>(smem_raw);
-    for (int i = threadIdx.x; i < kLut; i += blockDim.x)
-        lut[i] = make_double2(i ? rsqrt_pos((double)i) : 0.0, rsqrt_pos((double)i + 1.0));
+    LutRec *lut = reinterpret_cast<LutRec *>(smem_raw);
+    for (int i = threadIdx.x; i < kLut; i += blockDim.x) {
+        const double r0 = i ? rsqrt_pos((double)i) : 0.0, r1 = rsqrt_pos((double)i + 1.0);
+        LutRec t;
+        t.inv_n = r0 * r0; t.hn = p.c_h * r0; t.inv_n1 = r1 * r1; t.hn1 = p.c_h * r1;
+        lut[i] = t;
+    }
     __syncthreads();   // the only block-wide barrier (before any warp may leave)
 
     const long long inst = (long long)blockIdx.x * warps_per_cta + warp;
     if (inst >= p.n_inst) return;
 
     const int S = p.S, A = p.A, ncell = S * A;
-    Cell *cells = reinterpret_cast<Cell *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
-    double *smax = reinterpret_cast<double *>(cells + ncell);
-    double *sub2 = smax + S;
-    unsigned *cnt = reinterpret_cast<unsigned *>(sub2 + S);
-    int *sarg = reinterpret_cast<int *>(cnt + ncell);
-    int *actstep = sarg + S;
-    int *flushpt = actstep + S;
-    unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
+    StateRec *states = reinterpret_cast<StateRec *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
+    Cell *cells = reinterpret_cast<Cell *>(states + S);
+    unsigned *cnt = reinterpret_cast<unsigned *>(cells + ncell);
+    unsigned *hist = cnt + ncell;
 
     for (int c = lane; c < ncell; c += 32) {
         cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
@@ -190,55 +212,55 @@ __global__ void __launch_bounds__(256, 4) k_stream_rows(const StreamArgs p, cons
     {
         double m0, sec0; int g0;
         warp_top2(&cells[0].val, 3, A, m0, g0, sec0);   // every state starts identical
-        const double ub0 = runner_up_bound(sec0, m0);
-        for (int s = lane; s < S; s += 32) {
-            smax[s] = m0; sub2[s] = ub0; sarg[s] = g0; actstep[s] = -1; flushpt[s] = 0;   // ST1:58
-        }
+        StateRec st;
+        st.smax = m0; st.sub2 = runner_up_bound(sec0, m0); st.sarg = g0; st.actstep = -1; st.flushpt = 0; st.pad = 0;
+        for (int s = lane; s < S; s += 32) states[s] = st;                      // ST1:58
     }
     __syncwarp();
 
-    const unsigned lt = lanemask_lt(), le = lanemask_le(), gt = lanemask_gt();
+    const unsigned bit = 1u << lane;
+    const unsigned lt = bit - 1u, le = lt | bit, gt = ~le;
     const unsigned n_steps = p.n_steps;
     const long long row0 = inst * (long long)n_steps;
-    const int *gidx = p.idx + row0;
-    const int *gact = p.act + row0;
-    const RT *gR = reinterpret_cast<const RT *>(p.R) + row0;
-    OT *oval = reinterpret_cast<OT *>(p.out_value) + row0;
-    int *oact = p.out_act + row0;
-    OT *oall = OVERALL ? reinterpret_cast<OT *>(p.out_overall) + row0 : nullptr;
-    const double c_h = p.c_h, cap = p.cap, bonus = p.bonus;
+    const double cap = p.cap, bonus = p.bonus;
     const int rule = p.rule_act;
     const unsigned n_thres = (unsigned)p.n_thres;
+
+    // advancing per-lane pointers: inputs one batch ahead (software prefetch), outputs at the batch
+    const int *pi = p.idx + row0 + lane;
+    const int *pa = p.act + row0 + lane;
+    const RT *pr = reinterpret_cast<const RT *>(p.R) + row0 + lane;
+    OT *pv = reinterpret_cast<OT *>(p.out_value) + row0 + lane;
+    int *pg = p.out_act + row0 + lane;
+    OT *po = OVERALL ? reinterpret_cast<OT *>(p.out_overall) + row0 + lane : nullptr;
 
     double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
     unsigned bad = 0;     // lane-local count of out-of-range rows
 
-    // software prefetch: rows of batch b+1 are requested while batch b is processed
     int n_idx = 0, n_act = 0;
     RT n_R = RT(0);
-    if ((unsigned)lane < n_steps) { n_idx = ld_stream(gidx + lane); n_act = ld_stream(gact + lane); n_R = ld_stream(gR + lane); }
+    if ((unsigned)lane < n_steps) { n_idx = ld_stream(pi); n_act = ld_stream(pa); n_R = ld_stream(pr); }
 
-    for (unsigned k0 = 0; k0 < n_steps; k0 += 32) {
-        const unsigned k = k0 + lane;
-        const bool in_stream = k < n_steps;
+    for (unsigned k = lane; k - lane < n_steps; k += 32) {
+        const bool in_stream = k < n_steps;        // false only in the ragged last batch
         const int s_in = n_idx, a = n_act;
         const double r = (double)n_R;
-        {
-            const unsigned kn = k + 32;
-            if (kn < n_steps) { n_idx = ld_stream(gidx + kn); n_act = ld_stream(gact + kn); n_R = ld_stream(gR + kn); }
-        }
+        pi += 32; pa += 32; pr += 32;
+        if (k + 32 < n_steps) { n_idx = ld_stream(pi); n_act = ld_stream(pa); n_R = ld_stream(pr); }
         const bool active = in_stream && (unsigned)s_in < (unsigned)S && (unsigned)a < (unsigned)A;
         if (in_stream && !active) bad++;
-        // inactive lanes get a private key so they match nobody
+        // inactive lanes get a private key so they match nobody; their table index is clamped to 0
         const int s = active ? s_in : (0x40000000 | lane);
         const int key = active ? s_in * A + a : (0x40000000 | lane);
+        const int sx = active ? s_in : 0;
+        const int kx = active ? key : 0;
 
         // ---- phase 1: running moments of every row's cell, in time order -------------------
         const unsigned mk = __match_any_sync(FULL_MASK, key);
         const unsigned ms = __match_any_sync(FULL_MASK, s);
-        unsigned n0 = 0;
-        double acc1 = 0.0, acc2 = 0.0;
-        if (active) { n0 = cnt[key]; acc1 = cells[key].s1; acc2 = cells[key].s2; }
+        Cell *cell = cells + kx;
+        double acc1 = cell->s1, acc2 = cell->s2;
+        const unsigned n0 = cnt[kx];
         unsigned earlier = mk & lt;
         while (__any_sync(FULL_MASK, earlier != 0)) {
             const int j = earlier ? (__ffs(earlier) - 1) : lane;
@@ -249,84 +271,69 @@ __global__ void __launch_bounds__(256, 4) k_stream_rows(const StreamArgs p, cons
         acc2 = fma(r, r, acc2);
         const unsigned n = n0 + __popc(mk & lt) + 1u;
         __syncwarp();
-        if (active && (mk & gt) == 0) { cnt[key] = n; cells[key].s1 = acc1; cells[key].s2 = acc2; }
+        if (active && (mk & gt) == 0) { cnt[kx] = n; cell->s1 = acc1; cell->s2 = acc2; }
         const bool upd = active && n > n_thres;                                   // ST1:86
         double v;
         if (__all_sync(FULL_MASK, n < (unsigned)kLut)) {   // warp-uniform: no divergence around the table
-            const double2 rr = lut[n];
-            v = cell_value_rs(rr.x, rr.y, acc1, acc2, a == rule, c_h, cap);
+            v = cell_value_lut(lut[n], acc1, acc2, a == rule, cap);
         } else {
-            v = cell_value(n, acc1, acc2, a == rule, c_h, cap);
+            v = cell_value(n, acc1, acc2, a == rule, p.c_h, cap);
         }
 
         // ---- phase 2: per-row (max, argmax) of the row's state ----------------------------
-        double ms0 = 0.0, ub = 0.0;
-        int g = -1, ast = -1;
-        if (active) { ms0 = smax[s]; ub = sub2[s]; g = sarg[s]; ast = actstep[s]; }
-        const double smax0 = ms0;   // the state's max when the batch began (for overall_value)
-        double m_out;
-        int g_out = g;
-        {
-            // optimistic pass: nobody's argmax moves
-            const bool T = upd && a == g;   // row refreshes the argmax cell of its state
+        // Round 1 assumes nobody's argmax moves; a row that might move it is replayed exactly and
+        // the rows after it retry (rare).
+        StateRec *st = states + sx;
+        double smax0 = 0.0, m_out = 0.0;
+        int g_out = -1, ast = -1;
+        unsigned pend = __ballot_sync(FULL_MASK, active);
+        bool mine = active;
+        for (bool first = true;; first = false) {
+            const double c_ms0 = st->smax, c_ub = st->sub2;
+            const int c_g = st->sarg;
+            if (first) { smax0 = c_ms0; ast = st->actstep; }
+            const bool T = mine && upd && a == c_g;        // row refreshes the argmax cell of its state
             const unsigned tm = __ballot_sync(FULL_MASK, T);
             const unsigned cand = tm & ms & le;
             const int jl = cand ? (31 - __clz(cand)) : lane;
             const double vj = shfl_f64(v, jl);
-            m_out = cand ? vj : ms0;
-            const bool fail = upd && (T ? !(v > ub) : !(v <= ub && v < m_out));
-            if (__ballot_sync(FULL_MASK, fail) == 0) {
-                if (upd && (mk & gt) == 0) cells[key].val = v;
-                if (active && (ms & gt) == 0) smax[s] = m_out;
-            } else {
-                // ---- general path: finalize rows up to the first doubtful one, replay it exactly,
-                //      retry the rest (nothing was written by the optimistic pass) -------------------
-                unsigned pend = __ballot_sync(FULL_MASK, active);
-                bool mine = active;
-                while (pend) {
-                    double c_ms0 = 0.0, c_ub = 0.0;
-                    int c_g = -1;
-                    if (mine) { c_ms0 = smax[s]; c_g = sarg[s]; c_ub = sub2[s]; }
-                    const bool cT = mine && upd && a == c_g;
-                    const unsigned ctm = __ballot_sync(FULL_MASK, cT);
-                    const unsigned ccand = ctm & ms & le;
-                    const int cjl = ccand ? (31 - __clz(ccand)) : lane;
-                    const double cvj = shfl_f64(v, cjl);
-                    const double m_k = ccand ? cvj : c_ms0;
-                    const bool cfail = mine && upd && (cT ? !(v > c_ub) : !(v <= c_ub && v < m_k));
-                    const unsigned fm = __ballot_sync(FULL_MASK, cfail);
-                    const int j = fm ? (__ffs(fm) - 1) : 32;
-                    const unsigned fin = fm ? (pend & ((1u << j) - 1u)) : pend;
-                    if (mine && ((fin >> lane) & 1u)) {
-                        g_out = c_g; m_out = m_k;
-                        if (upd && (mk & fin & gt) == 0) cells[key].val = v;
-                        if ((ms & fin & gt) == 0) smax[s] = m_k;
-                    }
-                    if (fm == 0) break;
-                    __syncwarp();
-                    const int sj = __shfl_sync(FULL_MASK, s, j);
-                    const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
-                    if (lane == j) cells[key].val = v;
-                    __syncwarp();
-                    const int old_g = sarg[sj];
-                    double mx, second; int arg;
-                    warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
-                    if (arg != old_g) {
-                        // rows (flushpt, t_j) of this state were emitted with old_g: account for them
-                        unsigned csum = 0;
-                        for (int q = lane; q < A; q += 32) csum += cnt[sj * A + q];
-                        const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
-                        if (lane == j) { hist[old_g] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1; }
-                    }
-                    if (lane == j) {
-                        g_out = arg; m_out = mx;
-                        smax[sj] = mx; sarg[sj] = arg; sub2[sj] = runner_up_bound(second, mx);
-                    }
-                    __syncwarp();
-                    pend &= ~(fin | (1u << j));
-                    mine = mine && lane > j;
-                }
+            const double m_k = cand ? vj : c_ms0;
+            // a row keeps the argmax if it refreshes the argmax cell to above the runner-up bound, or
+            // another cell to at most that bound (and below the running max)
+            const bool fail = mine && upd && (T ? !(v > c_ub) : !(v <= c_ub && v < m_k));
+            const unsigned fm = __ballot_sync(FULL_MASK, fail);
+            const unsigned fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;   // pending rows before the first doubtful one
+            if (mine && (fin & bit)) {
+                g_out = c_g; m_out = m_k;
+                if (upd && (mk & fin & gt) == 0) cell->val = v;
+                if ((ms & fin & gt) == 0) st->smax = m_k;
             }
+            if (fm == 0) break;
+            // ---- exact replay of the first doubtful row j ------------------------------------
+            const int j = __ffs(fm) - 1;
+            __syncwarp();
+            const int sj = __shfl_sync(FULL_MASK, s, j);
+            const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
+            if (lane == j) cell->val = v;
+            __syncwarp();
+            const int old_g = states[sj].sarg;
+            double mx, second; int arg;
+            warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
+            if (arg != old_g) {
+                // rows (flushpt, t_j) of this state were emitted with old_g: account for them
+                unsigned csum = 0;
+                for (int q = lane; q < A; q += 32) csum += cnt[sj * A + q];
+                const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
+                if (lane == j) { hist[old_g] += (unsigned)(t_j - 1 - st->flushpt); st->flushpt = t_j - 1; }
+            }
+            if (lane == j) {
+                g_out = arg; m_out = mx;
+                st->smax = mx; st->sarg = arg; st->sub2 = runner_up_bound(second, mx);
+            }
+            __syncwarp();
+            pend &= ~(fin | (1u << j));
+            mine = mine && lane > j;
+            if (pend == 0) break;
         }
 
         // ---- activation step (ST1:98-99): first row of a state whose argmax is not the rule action
@@ -335,20 +342,21 @@ __global__ void __launch_bounds__(256, 4) k_stream_rows(const StreamArgs p, cons
             __syncwarp();
             if (need && lane == __ffs(need) - 1) {
                 unsigned csum = 0;
-                for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
-                actstep[s] = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
+                for (int q = 0; q < A; ++q) csum += cnt[sx * A + q];
+                st->actstep = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
             }
-            __syncwarp();
         }
         if (OVERALL) {                                                            // ST2:99-105
+            // contribution of the row's state after the row, minus before it; prefix-summed over the batch
             const bool act_before = ast != -1;
-            const bool act_now = act_before || (need & le) != 0;
-            const double c_k = (active && act_now) ? m_out + bonus : 0.0;
+            const bool act_now = active && (act_before || (need & le) != 0);
+            const double c_k = act_now ? m_out + bonus : 0.0;
             const unsigned prev = ms & lt;
             const int pl = prev ? (31 - __clz(prev)) : lane;
             const double c_prev_lane = shfl_f64(c_k, pl);
-            const double c_prev = prev ? c_prev_lane : (act_before ? smax0 + bonus : 0.0);
-            double d = active ? c_k - c_prev : 0.0;
+            const double c_start = act_before ? smax0 + bonus : 0.0;
+            double d = c_k - (prev ? c_prev_lane : c_start);
+            if (!active) d = 0.0;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const double o = __shfl_up_sync(FULL_MASK, d, off);
@@ -356,21 +364,23 @@ __global__ void __launch_bounds__(256, 4) k_stream_rows(const StreamArgs p, cons
             }
             const double ov = total + d;
             total += shfl_f64(d, 31);
-            if (in_stream) st_stream(oall + k, (OT)ov);
+            if (in_stream) st_stream(po, (OT)ov);
+            po += 32;
         }
         if (in_stream) {
-            st_stream(oval + k, active ? (OT)m_out : (OT)CUDART_NAN);
-            st_stream(oact + k, g_out);
+            st_stream(pv, active ? (OT)m_out : (OT)CUDART_NAN);
+            st_stream(pg, g_out);
         }
+        pv += 32; pg += 32;
         __syncwarp();   // table writes of this batch are ordered before the next batch's reads
     }
-    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)actstep[s];
+    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)states[s].actstep;
     if (p.act_hist != nullptr) {
         // rows since the last argmax change of each state carry the state's current argmax
         for (int s = lane; s < S; s += 32) {
             unsigned csum = 0;
             for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
-            atomicAdd(&hist[sarg[s]], csum - (unsigned)flushpt[s]);
+            atomicAdd(&hist[states[s].sarg], csum - (unsigned)states[s].flushpt);
         }
         __syncwarp();
         for (int a = lane; a < A; a += 32)
@@ -547,11 +557,11 @@ static const size_t kSmemPerSm = 228 * 1024;
 static int pick_warps_per_cta(long long n_inst, size_t wb, int sms) {
     int best = 1;
     long long best_cost = -1;
-    for (int w = 1; w <= 8; ++w) {
+    for (int w = 1; w <= kRowsMaxWarps; ++w) {
         const size_t cta = kRowsCtaFixedBytes + wb * w;
         if (cta > kMaxSmemPerCta) break;
         long long resident = (long long)(kSmemPerSm / (cta + 1024)) * w;   // warps per SM that fit
-        if (resident > 32) resident = 32;                                   // 64 registers per thread
+        if (resident > 28) resident = 28;                                   // 72 registers per thread
         const long long ctas = (n_inst + w - 1) / w;
         const long long per_sm = (ctas + sms - 1) / sms * w;                // warps the busiest SM runs
         const long long rounds = (per_sm + resident - 1) / resident;
