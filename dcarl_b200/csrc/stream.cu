@@ -46,7 +46,6 @@ struct StreamArgs {
     int n_thres, rule_act;
 };
 
-constexpr int kLut = 256;  // shared-memory table of {1/sqrt(n), 1/sqrt(n+1)} for n < kLut
 
 __device__ __forceinline__ double u32_to_double(unsigned n) {
     // exact for every uint32; avoids the slow I2F.F64 conversion path
@@ -94,12 +93,14 @@ __device__ __forceinline__ double cell_value(unsigned n, double s1, double s2, b
     return cell_value_rs(rsqrt_pos(dn), rsqrt_pos(dn + 1.0), s1, s2, is_rule, c_h, cap);
 }
 
-// Runner-up bound kept per state: any value in [second, max) keeps both fast-path
-// tests sound; the midpoint tolerates drift of either cell.
+// Runner-up bound kept per state: any value in [second, max) keeps both fast-path tests
+// sound.  It sits a quarter of the gap above the runner-up: lifting it when another cell
+// rises is cheap (see phase 2), replaying a row because the argmax cell dipped is not.
 __device__ __forceinline__ double runner_up_bound(double second, double mx) {
     if (second == -CUDART_INF) return second;
     if (!(second < mx)) return mx;
-    return 0.5 * second + 0.5 * mx;
+    const double b = fma(0.25, mx - second, second);
+    return b < mx ? b : second;
 }
 
 // ---- exact warp-wide max of doubles with integer reductions (REDUX) ---------------------------
@@ -144,39 +145,25 @@ __device__ __forceinline__ void warp_top2(const double *row, int stride, int A, 
 struct Cell {
     double s1, s2, val;
 };
-// per-state record: one 16-byte and one 8-byte shared load fetch everything a row needs
-struct __align__(16) StateRec {
+// per-state records, split so that the hot pair is one conflict-friendly 16-byte load
+struct __align__(16) StateHot {
     double smax;   // current max_a value[s][a]
     double sub2;   // runner-up bound: second-best <= sub2 < smax (== smax on an exact tie)
+};
+struct __align__(8) StateArg {
     int sarg;      // current first argmax
     int actstep;   // activation step, -1 = not yet (ST1:58)
-    int flushpt;   // rows of this state already counted in the action histogram
-    int pad;
-};
-// table entry for n < kLut: {1/n, c_h/sqrt(n), 1/(n+1), c_h/sqrt(n+1)}
-struct __align__(16) LutRec {
-    double inv_n, hn, inv_n1, hn1;
 };
 
 __host__ __device__ inline size_t rows_warp_bytes(int S, int A) {
     const size_t ncell = (size_t)S * A;
-    size_t b = (size_t)S * sizeof(StateRec) + ncell * sizeof(Cell) + ncell * sizeof(unsigned) +
-               (size_t)A * sizeof(unsigned);   // states, cells, cnt, per-warp action histogram
+    size_t b = (size_t)S * (sizeof(StateHot) + sizeof(StateArg) + sizeof(int))   // hot, arg, flushpt
+               + ncell * sizeof(Cell) + ncell * sizeof(unsigned)                   // cells, cnt
+               + (size_t)A * sizeof(unsigned);                                     // per-warp action histogram
     return (b + 15) & ~(size_t)15;
 }
-constexpr size_t kRowsCtaFixedBytes = kLut * sizeof(LutRec);
+constexpr size_t kRowsCtaFixedBytes = 0;
 constexpr int kRowsMaxWarps = 7;
-
-// closed form with the table entries (see cell_value_rs)
-__device__ __forceinline__ double cell_value_lut(const LutRec &t, double s1, double s2, bool is_rule, double cap) {
-    const double mean = s1 * t.inv_n;
-    const double ub = dmin(cap, mean + t.hn);
-    const double var = fma(s2, t.inv_n, -mean * mean);
-    const double sigma = var > 1e-280 ? var * rsqrt_pos(var) : 0.0;
-    const double lb = mean - t.hn;
-    const double ci = fma(fma(-4.0, sigma, mean) + s1, t.inv_n1, -t.hn1);
-    return is_rule ? ub : dmin(lb, ci);
-}
 
 template <typename RT, typename OT, bool OVERALL>
 __global__ void __launch_bounds__(kRowsMaxWarps * 32, 4)
@@ -185,23 +172,16 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
 
-    LutRec *lut = reinterpret_cast<LutRec *>(smem_raw);
-    for (int i = threadIdx.x; i < kLut; i += blockDim.x) {
-        const double r0 = i ? rsqrt_pos((double)i) : 0.0, r1 = rsqrt_pos((double)i + 1.0);
-        LutRec t;
-        t.inv_n = r0 * r0; t.hn = p.c_h * r0; t.inv_n1 = r1 * r1; t.hn1 = p.c_h * r1;
-        lut[i] = t;
-    }
-    __syncthreads();   // the only block-wide barrier (before any warp may leave)
-
     const long long inst = (long long)blockIdx.x * warps_per_cta + warp;
     if (inst >= p.n_inst) return;
 
     const int S = p.S, A = p.A, ncell = S * A;
-    StateRec *states = reinterpret_cast<StateRec *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
-    Cell *cells = reinterpret_cast<Cell *>(states + S);
+    StateHot *hot = reinterpret_cast<StateHot *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
+    StateArg *sargs = reinterpret_cast<StateArg *>(hot + S);
+    Cell *cells = reinterpret_cast<Cell *>(sargs + S);
     unsigned *cnt = reinterpret_cast<unsigned *>(cells + ncell);
-    unsigned *hist = cnt + ncell;
+    int *flushpt = reinterpret_cast<int *>(cnt + ncell);
+    unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
 
     for (int c = lane; c < ncell; c += 32) {
         cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
@@ -212,41 +192,46 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     {
         double m0, sec0; int g0;
         warp_top2(&cells[0].val, 3, A, m0, g0, sec0);   // every state starts identical
-        StateRec st;
-        st.smax = m0; st.sub2 = runner_up_bound(sec0, m0); st.sarg = g0; st.actstep = -1; st.flushpt = 0; st.pad = 0;
-        for (int s = lane; s < S; s += 32) states[s] = st;                      // ST1:58
+        StateHot h0;
+        h0.smax = m0; h0.sub2 = runner_up_bound(sec0, m0);
+        StateArg a0;
+        a0.sarg = g0; a0.actstep = -1;                                          // ST1:58
+        for (int s = lane; s < S; s += 32) { hot[s] = h0; sargs[s] = a0; flushpt[s] = 0; }
     }
     __syncwarp();
 
     const unsigned bit = 1u << lane;
     const unsigned lt = bit - 1u, le = lt | bit, gt = ~le;
     const unsigned n_steps = p.n_steps;
-    const long long row0 = inst * (long long)n_steps;
-    const double cap = p.cap, bonus = p.bonus;
+    const double c_h = p.c_h, cap = p.cap, bonus = p.bonus;
     const int rule = p.rule_act;
     const unsigned n_thres = (unsigned)p.n_thres;
 
-    // advancing per-lane pointers: inputs one batch ahead (software prefetch), outputs at the batch
-    const int *pi = p.idx + row0 + lane;
-    const int *pa = p.act + row0 + lane;
-    const RT *pr = reinterpret_cast<const RT *>(p.R) + row0 + lane;
-    OT *pv = reinterpret_cast<OT *>(p.out_value) + row0 + lane;
-    int *pg = p.out_act + row0 + lane;
-    OT *po = OVERALL ? reinterpret_cast<OT *>(p.out_overall) + row0 + lane : nullptr;
+    // One 32-bit element index addresses all six arrays (the host keeps n_inst*n_steps of a launch
+    // below 2^32): an address is a single IMAD.WIDE off a constant-bank base, no live pointers.
+    const int *__restrict__ gidx = p.idx;
+    const int *__restrict__ gact = p.act;
+    const RT *__restrict__ gR = reinterpret_cast<const RT *>(p.R);
+    OT *__restrict__ oval = reinterpret_cast<OT *>(p.out_value);
+    int *__restrict__ oact = p.out_act;
+    OT *__restrict__ oall = reinterpret_cast<OT *>(p.out_overall);
+    const unsigned ebase = (unsigned)inst * n_steps + lane;
 
     double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
     unsigned bad = 0;     // lane-local count of out-of-range rows
 
+    // software prefetch: rows of batch b+1 are requested while batch b is processed
     int n_idx = 0, n_act = 0;
     RT n_R = RT(0);
-    if ((unsigned)lane < n_steps) { n_idx = ld_stream(pi); n_act = ld_stream(pa); n_R = ld_stream(pr); }
+    if ((unsigned)lane < n_steps) { n_idx = ld_stream(gidx + ebase); n_act = ld_stream(gact + ebase); n_R = ld_stream(gR + ebase); }
 
     for (unsigned k = lane; k - lane < n_steps; k += 32) {
         const bool in_stream = k < n_steps;        // false only in the ragged last batch
         const int s_in = n_idx, a = n_act;
-        const double r = (double)n_R;
-        pi += 32; pa += 32; pr += 32;
-        if (k + 32 < n_steps) { n_idx = ld_stream(pi); n_act = ld_stream(pa); n_R = ld_stream(pr); }
+        const RT rin = n_R;
+        const double r = (double)rin;
+        const unsigned e = ebase + (k - lane);
+        if (k + 32 < n_steps) { n_idx = ld_stream(gidx + e + 32); n_act = ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
         const bool active = in_stream && (unsigned)s_in < (unsigned)S && (unsigned)a < (unsigned)A;
         if (in_stream && !active) bad++;
         // inactive lanes get a private key so they match nobody; their table index is clamped to 0
@@ -261,11 +246,24 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         Cell *cell = cells + kx;
         double acc1 = cell->s1, acc2 = cell->s2;
         const unsigned n0 = cnt[kx];
+        // the state records are not touched by phase 1: fetch them now, under its latency
+        StateHot *sh = hot + sx;
+        StateArg *sa = sargs + sx;
+        StateHot h = *sh;
+        StateArg ga = *sa;
         unsigned earlier = mk & lt;
+        {
+            // the two oldest peers straight-line (independent shuffles), a loop only beyond that
+            const unsigned e1 = earlier & (earlier - 1);
+            const RT r1 = __shfl_sync(FULL_MASK, rin, earlier ? (__ffs(earlier) - 1) : lane);
+            const RT r2 = __shfl_sync(FULL_MASK, rin, e1 ? (__ffs(e1) - 1) : lane);
+            if (earlier) { const double x = (double)r1; acc1 += x; acc2 = fma(x, x, acc2); }
+            if (e1) { const double x = (double)r2; acc1 += x; acc2 = fma(x, x, acc2); }
+            earlier = e1 & (e1 - 1);
+        }
         while (__any_sync(FULL_MASK, earlier != 0)) {
-            const int j = earlier ? (__ffs(earlier) - 1) : lane;
-            const double rj = shfl_f64(r, j);
-            if (earlier) { acc1 += rj; acc2 = fma(rj, rj, acc2); earlier &= earlier - 1; }
+            const RT rj = __shfl_sync(FULL_MASK, rin, earlier ? (__ffs(earlier) - 1) : lane);
+            if (earlier) { const double x = (double)rj; acc1 += x; acc2 = fma(x, x, acc2); earlier &= earlier - 1; }
         }
         acc1 += r;
         acc2 = fma(r, r, acc2);
@@ -273,25 +271,20 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         __syncwarp();
         if (active && (mk & gt) == 0) { cnt[kx] = n; cell->s1 = acc1; cell->s2 = acc2; }
         const bool upd = active && n > n_thres;                                   // ST1:86
-        double v;
-        if (__all_sync(FULL_MASK, n < (unsigned)kLut)) {   // warp-uniform: no divergence around the table
-            v = cell_value_lut(lut[n], acc1, acc2, a == rule, cap);
-        } else {
-            v = cell_value(n, acc1, acc2, a == rule, p.c_h, cap);
-        }
+        const double v = cell_value(n, acc1, acc2, a == rule, c_h, cap);
 
         // ---- phase 2: per-row (max, argmax) of the row's state ----------------------------
         // Round 1 assumes nobody's argmax moves; a row that might move it is replayed exactly and
         // the rows after it retry (rare).
-        StateRec *st = states + sx;
-        double smax0 = 0.0, m_out = 0.0;
-        int g_out = -1, ast = -1;
+        const double smax0 = h.smax;   // the state's max when the batch began (for overall_value)
+        const int ast = ga.actstep;
+        double m_out = 0.0;
+        int g_out = -1;
         unsigned pend = __ballot_sync(FULL_MASK, active);
         bool mine = active;
-        for (bool first = true;; first = false) {
-            const double c_ms0 = st->smax, c_ub = st->sub2;
-            const int c_g = st->sarg;
-            if (first) { smax0 = c_ms0; ast = st->actstep; }
+        for (;;) {
+            const double c_ms0 = h.smax, c_ub = h.sub2;
+            const int c_g = ga.sarg;
             const bool T = mine && upd && a == c_g;        // row refreshes the argmax cell of its state
             const unsigned tm = __ballot_sync(FULL_MASK, T);
             const unsigned cand = tm & ms & le;
@@ -300,13 +293,19 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const double m_k = cand ? vj : c_ms0;
             // a row keeps the argmax if it refreshes the argmax cell to above the runner-up bound, or
             // another cell to at most that bound (and below the running max)
-            const bool fail = mine && upd && (T ? !(v > c_ub) : !(v <= c_ub && v < m_k));
+            bool fail = mine && upd && (T ? !(v > c_ub) : !(v <= c_ub && v < m_k));
+            // a non-argmax row that rises above the bound but stays below the max keeps the argmax; it
+            // is now the exact runner-up (v > bound >= every other cell).  If no later row of its
+            // state follows in this batch it re-centres the bound itself instead of forcing a replay.
+            const bool lift = fail && !T && v < m_k && (ms & gt) == 0;
+            if (lift) fail = false;
             const unsigned fm = __ballot_sync(FULL_MASK, fail);
             const unsigned fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;   // pending rows before the first doubtful one
             if (mine && (fin & bit)) {
                 g_out = c_g; m_out = m_k;
                 if (upd && (mk & fin & gt) == 0) cell->val = v;
-                if ((ms & fin & gt) == 0) st->smax = m_k;
+                if ((ms & fin & gt) == 0) sh->smax = m_k;
+                if (lift) sh->sub2 = runner_up_bound(v, m_k);
             }
             if (fm == 0) break;
             // ---- exact replay of the first doubtful row j ------------------------------------
@@ -316,7 +315,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
             if (lane == j) cell->val = v;
             __syncwarp();
-            const int old_g = states[sj].sarg;
+            const int old_g = sargs[sj].sarg;
             double mx, second; int arg;
             warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
             if (arg != old_g) {
@@ -324,16 +323,18 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 unsigned csum = 0;
                 for (int q = lane; q < A; q += 32) csum += cnt[sj * A + q];
                 const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
-                if (lane == j) { hist[old_g] += (unsigned)(t_j - 1 - st->flushpt); st->flushpt = t_j - 1; }
+                if (lane == j) { hist[old_g] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1; }
             }
             if (lane == j) {
                 g_out = arg; m_out = mx;
-                st->smax = mx; st->sarg = arg; st->sub2 = runner_up_bound(second, mx);
+                sh->smax = mx; sh->sub2 = runner_up_bound(second, mx); sa->sarg = arg;
             }
             __syncwarp();
             pend &= ~(fin | (1u << j));
             mine = mine && lane > j;
             if (pend == 0) break;
+            h = *sh;
+            ga = *sa;
         }
 
         // ---- activation step (ST1:98-99): first row of a state whose argmax is not the rule action
@@ -343,7 +344,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             if (need && lane == __ffs(need) - 1) {
                 unsigned csum = 0;
                 for (int q = 0; q < A; ++q) csum += cnt[sx * A + q];
-                st->actstep = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
+                sa->actstep = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
             }
         }
         if (OVERALL) {                                                            // ST2:99-105
@@ -364,23 +365,21 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             }
             const double ov = total + d;
             total += shfl_f64(d, 31);
-            if (in_stream) st_stream(po, (OT)ov);
-            po += 32;
+            if (in_stream) st_stream(oall + e, (OT)ov);
         }
         if (in_stream) {
-            st_stream(pv, active ? (OT)m_out : (OT)CUDART_NAN);
-            st_stream(pg, g_out);
+            st_stream(oval + e, active ? (OT)m_out : (OT)CUDART_NAN);
+            st_stream(oact + e, g_out);
         }
-        pv += 32; pg += 32;
         __syncwarp();   // table writes of this batch are ordered before the next batch's reads
     }
-    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)states[s].actstep;
+    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)sargs[s].actstep;
     if (p.act_hist != nullptr) {
         // rows since the last argmax change of each state carry the state's current argmax
         for (int s = lane; s < S; s += 32) {
             unsigned csum = 0;
             for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
-            atomicAdd(&hist[states[s].sarg], csum - (unsigned)states[s].flushpt);
+            atomicAdd(&hist[sargs[s].sarg], csum - (unsigned)flushpt[s]);
         }
         __syncwarp();
         for (int a = lane; a < A; a += 32)
@@ -583,9 +582,21 @@ static int launch_rows(const StreamArgs &a, cudaStream_t st) {
         DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = kMaxSmemPerCta;
     }
-    const long long grid = (a.n_inst + wpc - 1) / wpc;
-    kern<<<(unsigned)grid, wpc * 32, smem, st>>>(a, wpc, (unsigned)wb);
-    DCARL_LAUNCH_CHECK("k_stream_rows");
+    // the kernel indexes rows with 32 bits: launch in instance chunks of < 2^32 rows each
+    const long long max_inst = a.n_steps ? (long long)(0xffffff00u / a.n_steps) : a.n_inst;
+    for (long long lo = 0; lo < a.n_inst; lo += max_inst) {
+        StreamArgs c = a;
+        c.n_inst = a.n_inst - lo < max_inst ? a.n_inst - lo : max_inst;
+        const long long off = lo * (long long)a.n_steps;
+        c.idx = a.idx + off; c.act = a.act + off; c.out_act = a.out_act + off;
+        c.R = reinterpret_cast<const RT *>(a.R) + off;
+        c.out_value = reinterpret_cast<OT *>(a.out_value) + off;
+        if (OV) c.out_overall = reinterpret_cast<OT *>(a.out_overall) + off;
+        c.out_activation = a.out_activation + lo * a.S;
+        const long long grid = (c.n_inst + wpc - 1) / wpc;
+        kern<<<(unsigned)grid, wpc * 32, smem, st>>>(c, wpc, (unsigned)wb);
+        DCARL_LAUNCH_CHECK("k_stream_rows");
+    }
     return 0;
 }
 
