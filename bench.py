@@ -389,7 +389,7 @@ def cpu_legs(plan, idx, act, R):
     inputs (first instances of rank 0), cross-checked against the GPU's argmax traces."""
     cores = _cores()
     procs = min(cores, 64)
-    n_lit = min(idx.shape[0], 3 * procs)
+    n_lit = min(idx.shape[0], 12 * procs)       # ~10-15 s of CPU work
     hi, ha, hr = idx[:n_lit].cpu().numpy(), act[:n_lit].cpu().numpy(), R[:n_lit].cpu().numpy()
     gpu_act = plan.act[:n_lit].cpu().numpy()
     v_lit, acts_lit, dt_lit = cpu_literal(hi, ha, hr, procs)
