@@ -13,7 +13,7 @@ There is no CPU fallback: a compute call without the built library or without a 
 """
 from ._abi import DcarlError, Params, RlsParams, build, LIB_PATH  # noqa: F401
 from .bounds import CI_lower_bound, bounds_batch, cell_values, lower_bound, mean_value, upper_bound  # noqa: F401
-from .stream import StreamPlan, StreamResult, simulate, stream_bounds  # noqa: F401
+from .stream import StreamPlan, StreamResult, merge_stats, simulate, stream_bounds  # noqa: F401
 from .sampling import (Data_Generation, add_an_act_data, generate, random_state_manual,  # noqa: F401
                        random_state_norm, sample_returns, sample_returns_philox)
 from .rls import RLS, BoxBuffer, VISITED_STATE_DIST  # noqa: F401

@@ -54,3 +54,24 @@ def allreduce_max(t, group=None):
 def barrier():
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
+
+
+def box_query_sharded(buf, queries, n_actions, rls_params=None, group=None):
+    """Config-4 pattern: the {state, action, return} buffer is ROW-sharded (each rank's ``buf`` holds
+    M/G rows), the queries are replicated.  Every rank scans its shard once, the raw moments
+    (n, sum R, sum R^2) [Q, n_actions, 3] are summed across ranks with ONE all-reduce, and every
+    rank runs the small select epilogue redundantly (no broadcast).  Returns CUDA tensors
+    (moments, mean_var, action)."""
+    mom = buf.moments(queries, n_actions)
+    allreduce_stats(mom, group)
+    mv, pick = buf.select(mom, rls_params)
+    return mom, mv, pick
+
+
+def stream_sharded(plan, idx, act, R, group=None):
+    """Config-2/5 pattern: scenario instances are block-partitioned over ranks (``plan`` and the
+    inputs are this rank's shard, see ``shard_range``); no data-path exchange, one all-reduce of the
+    summary statistics.  Returns (this rank's StreamResult, all-reduced stats)."""
+    res = plan.run_device(idx, act, R)
+    allreduce_stats(res.stats, group)
+    return res, res.stats

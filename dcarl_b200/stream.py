@@ -235,3 +235,14 @@ def simulate(data, true_action_values, state_num, action_num, rule_act=0, n_thre
         activation_step=res.activation_step.copy(),
         overall_value=res.overall.tolist(),
         step_value_rows=res.value, step_act_rows=res.act)
+
+
+def merge_stats(stats_list, A_max=None):
+    """Sum the summary vectors of several groups of instances whose action counts differ (BASELINE
+    config 5 mixes Simulation_1-shaped S=1/A=30 and Simulation_2-shaped S=20/A=11 scenarios): the
+    action histogram tail is zero-padded to the widest group.  Tensors in -> tensor out."""
+    A_max = A_max or max(int(st.numel()) - STATS_HEADER for st in stats_list)
+    out = torch.zeros(STATS_HEADER + A_max, dtype=torch.float64, device=stats_list[0].device)
+    for st in stats_list:
+        out[:st.numel()] += st
+    return out

@@ -79,3 +79,32 @@ def test_two_rank_gloo_allreduce_matches_single_process():
         assert mx == 2.0
         assert np.array_equal(acts, full["act"][lo:hi])            # per-scenario outputs do not depend on the sharding
     assert np.array_equal(got[0][3], got[1][3])                    # every rank holds the same reduced vector
+
+
+def test_row_sharded_box_moments_sum_to_the_unsharded_answer(golden):
+    """raw moments (n, sum, sum^2) of row shards add up; the select epilogue on the
+    summed moments equals the unsharded pick (host logic, oracle as the per-shard scanner)."""
+    import numpy as np
+    from dcarl_b200.dist import shard_range
+    from oracle import cport
+    g = golden("rls_box")
+    vs, ret, dr, dist = g["visited_state"], g["visited_value"][:, 1], g["driving_record"], g["dist"]
+    q = dr[::7, :20]
+    full = cport.box_moments(vs, ret, dist, q, 8)
+
+    def raw(nmv_rows_state, nmv_rows_ret):
+        nmv = cport.box_moments(nmv_rows_state, nmv_rows_ret, dist, q, 8)
+        n = nmv[:, :, 0]
+        s1 = np.where(n > 0, nmv[:, :, 1] * n, 0.0)
+        s2 = np.where(n > 0, (nmv[:, :, 2] + nmv[:, :, 1] ** 2) * n, 0.0)
+        return np.stack([n, s1, s2], -1)
+    tot = np.zeros((len(q), 8, 3))
+    for r in range(8):
+        lo, hi = shard_range(len(vs), r, 8)
+        tot += raw(vs[lo:hi], ret[lo:hi])
+    n = tot[:, :, 0]
+    assert np.array_equal(n, full[:, :, 0])
+    mean = np.where(n > 0, tot[:, :, 1] / np.maximum(n, 1), -1.0)
+    var = np.where(n > 0, np.maximum(tot[:, :, 2] / np.maximum(n, 1) - mean ** 2, 0.0), -1.0)
+    assert np.abs(mean - full[:, :, 1]).max() < 1e-12 and np.abs(var - full[:, :, 2]).max() < 1e-12
+    assert np.array_equal(cport.box_select(np.stack([n, mean, var], -1)), cport.box_select(full))

@@ -172,3 +172,30 @@ def test_full_size_config2_properties_and_sampled_parity():
         astep, ov = recompute_from_traces(hi[j], sub.value[j].astype(np.float64), sub.act[j], S)
         assert np.array_equal(astep, sub.activation_step[j])
         assert np.abs(ov - sub.overall[j]).max() < 1e-2 * 1e-1   # float32 traces: 20 states x ~6e-6 each
+
+
+def test_config5_mixed_sim1_sim2_batch_reduced():
+    """BASELINE config 5 at reduced size: even instances Simulation_1-shaped (S=1, A=30, 11 live
+    actions), odd instances Simulation_2-shaped (S=20, A=11), 500 steps; one merged stats vector."""
+    n_each, n_steps = 96, 500
+    i1, a1, R1 = synth_streams(n_each, n_steps, 1, 30, seed=4000, r_dtype=np.float32, live_actions=11)
+    i2, a2, R2 = synth_streams(n_each, n_steps, 20, 11, seed=4001, r_dtype=np.float32)
+    p1 = dc.StreamPlan(n_each, n_steps, 1, 30)
+    p2 = dc.StreamPlan(n_each, n_steps, 20, 11)
+    r1 = p1.run_device(*[torch.from_numpy(x).cuda() for x in (i1, a1, R1)])
+    r2 = p2.run_device(*[torch.from_numpy(x).cuda() for x in (i2, a2, R2)])
+    merged = dc.merge_stats([r1.stats, r2.stats]).cpu().numpy()
+    want = np.zeros(5 + 30)
+    for (ii, aa, RR, S, A, res) in ((i1, a1, R1, 1, 30, r1), (i2, a2, R2, 20, 11, r2)):
+        ref = _oracle(ii, aa, RR.astype(np.float64), S, A)
+        class _R:
+            pass
+        h = _R()
+        h.value, h.act = res.value.cpu().numpy(), res.act.cpu().numpy()
+        h.overall, h.activation_step = res.overall.cpu().numpy(), res.activation_step.cpu().numpy()
+        compare_stream(h, ref, value_tol=1e-5)
+        st = stats_reference(ref["value"].astype(np.float32), ref["overall"].astype(np.float32),
+                             ref["activation_step"], ref["act"], A)
+        want[:5 + A] += st
+    assert np.array_equal(merged[2:], want[2:])
+    assert np.allclose(merged[:2], want[:2], rtol=1e-6)
