@@ -352,7 +352,13 @@ def secondary(dev, peak):
         out[f"box_moments_Q{Q}"] = {"rows": M, "n_actions": NA, "ms": ms, "rows_per_s": M / (ms * 1e-3),
                                     "queries_per_s": Q / (ms * 1e-3), "achieved_GBs": gbs, "frac": gbs / peak,
                                     "algorithmic_bytes_per_row": 88, "matched_rows": float(mom[:, :, 0].sum())}
-    del buf
+    run = buf.query_graph(1, NA)
+    q1 = centers[:1].double().contiguous()
+    ms = timed(lambda: run(q1), 50)
+    out["box_query_graph_Q1"] = {"rows": M, "ms": ms, "queries_per_s": 1 / (ms * 1e-3), "achieved_GBs": M * 88 / (ms * 1e-3) / 1e9,
+                                 "frac": M * 88 / (ms * 1e-3) / 1e9 / peak,
+                                 "note": "whole act_test query as one CUDA-graph replay: query upload + zero + prepare + scan + select"}
+    del buf, run
     # config 3 mode A: 65 536 episodes x 200 draws, deviates supplied (16 B/row) and on-device Philox (12 B/row)
     n = 65536 * 200
     qs = torch.rand((20, 11), generator=g, device=dev) * 150 - 50

@@ -301,6 +301,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             if (lift) fail = false;
             const unsigned fm = __ballot_sync(FULL_MASK, fail);
             const unsigned fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;   // pending rows before the first doubtful one
+            __syncwarp();   // every lane has consumed its state record before a peer overwrites it
             if (mine && (fin & bit)) {
                 g_out = c_g; m_out = m_k;
                 if (upd && (mk & fin & gt) == 0) cell->val = v;

@@ -81,14 +81,25 @@ class BoxBuffer:
                                        _dev.ptr(self._ws), self._ws.numel(), _dev.stream_handle(stream)))
         return out
 
-    def select(self, moments, rls_params=None, stream=None):
+    def select(self, moments, rls_params=None, stream=None, out=None):
         """moments [Q, n_actions, 3] -> (mean_var CUDA float64 [Q, n_actions, 2], action CUDA int32 [Q])."""
         Q, na, _ = moments.shape
-        mv = torch.empty((Q, na, 2), dtype=torch.float64, device=self.device)
-        pick = torch.empty((Q,), dtype=torch.int32, device=self.device)
+        if out is None:
+            mv = torch.empty((Q, na, 2), dtype=torch.float64, device=self.device)
+            pick = torch.empty((Q,), dtype=torch.int32, device=self.device)
+        else:
+            mv, pick = out
         _abi.check(_abi.lib().dcarl_box_select(_dev.ptr(moments), Q, na, rls_params or _abi.RlsParams(),
                                                _dev.ptr(mv), _dev.ptr(pick), _dev.stream_handle(stream)))
         return mv, pick
+
+    def query_graph(self, Q, n_actions=8, rls_params=None):
+        """A CUDA-graph replay of (zero moments, threshold prepare, scan, select) for repeated queries
+        of one shape: the per-query cost is one graph launch instead of four kernel launches plus
+        their host overhead (the scan of a 1e7-row shard is ~0.15 ms, shorter than that overhead).
+        Returns ``run(queries) -> (moments, mean_var, action)`` writing into static CUDA tensors; the
+        graph is re-captured automatically when rows were appended to the buffer."""
+        return _BoxQueryGraph(self, int(Q), int(n_actions), rls_params or _abi.RlsParams())
 
     def query(self, obs, n_actions=8, rls_params=None):
         """obs [D] or [Q, D] -> host (n [Q, A], mean [Q, A], var [Q, A], action [Q])."""
@@ -96,6 +107,35 @@ class BoxBuffer:
         mv, pick = self.select(mom, rls_params)
         mom_h, mv_h = mom.cpu().numpy(), mv.cpu().numpy()
         return mom_h[:, :, 0], mv_h[:, :, 0], mv_h[:, :, 1], pick.cpu().numpy()
+
+
+class _BoxQueryGraph:
+    def __init__(self, buf, Q, n_actions, rls_params):
+        self.buf, self.Q, self.na, self.rp = buf, Q, n_actions, rls_params
+        dev = buf.device
+        self.q = torch.zeros((Q, buf.D), dtype=torch.float64, device=dev)
+        self.mom = torch.empty((Q, n_actions, 3), dtype=torch.float64, device=dev)
+        self.mv = torch.empty((Q, n_actions, 2), dtype=torch.float64, device=dev)
+        self.pick = torch.empty((Q,), dtype=torch.int32, device=dev)
+        self._graph, self._rows = None, -1
+
+    def _record(self):
+        buf = self.buf
+        buf.moments(self.q, self.na, out=self.mom)            # sizes the workspace outside the capture
+        buf.select(self.mom, self.rp, out=(self.mv, self.pick))
+        torch.cuda.synchronize(buf.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            buf.moments(self.q, self.na, out=self.mom)
+            buf.select(self.mom, self.rp, out=(self.mv, self.pick))
+        self._graph, self._rows = g, len(buf)
+
+    def __call__(self, queries):
+        if self._graph is None or self._rows != len(self.buf):
+            self._record()
+        self.q.copy_(_dev.as_device(queries, torch.float64, self.buf.device).reshape(self.Q, self.buf.D), non_blocking=True)
+        self._graph.replay()
+        return self.mom, self.mv, self.pick
 
 
 class RLS(object):

@@ -182,3 +182,22 @@ def test_rls_class_drop_in(tmp_path, golden, monkeypatch):
     # should_use_rule: under-visited rule action -> rule
     rls.is_training = True
     assert int(rls.act(far, np.array(5))) == 0
+
+
+def test_query_graph_replay_matches_the_plain_path_and_tracks_appends():
+    rng = np.random.default_rng(21)
+    centers, vs, ret = _clustered(rng, n_centers=5)
+    buf = dc.BoxBuffer(20)
+    half = len(vs) // 2
+    buf.append(vs[:half], ret[:half])
+    run = buf.query_graph(len(centers), 8)
+    for upto in (half, len(vs)):
+        mom, mv, pick = run(centers)
+        torch.cuda.synchronize()
+        n, mean, var, p = buf.query(centers, 8)
+        assert np.array_equal(mom[:, :, 0].cpu().numpy(), n) and np.array_equal(pick.cpu().numpy(), p)
+        assert np.allclose(mv[:, :, 0].cpu().numpy(), mean, rtol=0, atol=1e-12)
+        ref = _oracle_nmv(vs[:upto], ret[:upto], centers, 8)
+        assert np.array_equal(n, ref[:, :, 0])
+        if upto == half:
+            buf.append(vs[half:], ret[half:])          # the next call must re-capture with the new row count

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Small invocations of every kernel, meant to run under compute-sanitizer:
+    compute-sanitizer --tool memcheck  python tools/sanitize_cases.py
+    compute-sanitizer --tool racecheck python tools/sanitize_cases.py
+Results are also checked against the oracle so a silent corruption fails the run."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dcarl_b200 as dc  # noqa: E402
+from helpers import compare_stream, synth_streams  # noqa: E402
+from oracle import cport  # noqa: E402
+
+for (n_inst, n_steps, S, A, kw) in [(9, 700, 20, 11, {}), (5, 333, 1, 30, {}), (3, 200, 3, 40, {}), (4, 300, 40, 5, {"rule_act": 3})]:
+    idx, act, R = synth_streams(n_inst, n_steps, S, A, seed=n_steps, r_dtype=np.float64)
+    ref = cport.stream(idx, act, R, S, A, cport.default_params(**kw))
+    for variant in (0, 1):
+        res = dc.stream_bounds(idx, act, R, S, A, dc.Params(**kw), variant=variant, want_stats=True)
+        compare_stream(res, ref, value_tol=1e-9)
+print("stream ok")
+rng = np.random.default_rng(0)
+dist = dc.VISITED_STATE_DIST[0]
+vs = np.hstack([rng.normal(0, 0.4, (3001, 20)) * dist[:20], rng.integers(0, 8, (3001, 1)).astype(np.float64)])
+ret = -rng.random(3001)
+buf = dc.BoxBuffer(20, capacity=64)
+buf.append(vs, ret)
+for Q in (1, 7):
+    q = vs[:Q, :20]
+    n, mean, var, pick = buf.query(q, 8)
+    ref = cport.box_moments(vs.astype(np.float32).astype(np.float64), ret.astype(np.float32).astype(np.float64), dist, q, 8)
+    assert np.array_equal(n, ref[:, :, 0])
+run = buf.query_graph(1, 8)
+run(vs[:1, :20])
+print("box ok")
+x = [rng.normal(0, 50, n) for n in (1, 17, 300, 5000)]
+got = dc.bounds_batch(x)
+assert np.allclose(got[2], cport.bounds(x[2]), rtol=1e-12)
+dc.cell_values([12, 40], [100.0, -50.0], [2000.0, 900.0], [0, 2])
+z = rng.standard_normal(5000)
+dc.sample_returns(rng.uniform(-50, 100, (20, 11)), z, rng.integers(0, 11, 5000), rng.standard_normal(5000))
+dc.sample_returns_philox(torch.rand((20, 11), device="cuda"), 5000, 3)
+s0 = rng.uniform(-5, 5, (1000, 20)).astype(np.float32)
+dc.rollout_cv(s0, rng.integers(0, 11, 1000))
+torch.cuda.synchronize()
+print("all kernels ran")
