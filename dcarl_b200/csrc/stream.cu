@@ -24,6 +24,8 @@
 //                    at a time with lanes over actions.  Fallback + cross-check.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dcarl {
@@ -225,20 +227,26 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     RT n_R = RT(0);
     if ((unsigned)lane < n_steps) { n_idx = ld_stream(gidx + ebase); n_act = ld_stream(gact + ebase); n_R = ld_stream(gR + ebase); }
 
-    for (unsigned k = lane; k - lane < n_steps; k += 32) {
-        const bool in_stream = k < n_steps;        // false only in the ragged last batch
-        const int s_in = n_idx, a = n_act;
+    // One batch of 32 rows.  TAIL = the ragged last batch (lanes past the end of the stream are
+    // inactive); full batches compile without any of the activity predicates.
+    auto batch = [&](auto tail_tag, const unsigned k) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const bool in_stream = TAIL ? (k < n_steps) : true;
+        // out-of-range idx / act are clamped (memory safety) and counted: bad_rows != 0 is an error
+        // for the caller, the outputs of such an instance are unspecified
+        const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
+        const int a = (int)min((unsigned)n_act, (unsigned)(A - 1));
+        if (in_stream && (s_in != n_idx || a != n_act)) bad++;
         const RT rin = n_R;
         const double r = (double)rin;
         const unsigned e = ebase + (k - lane);
         if (k + 32 < n_steps) { n_idx = ld_stream(gidx + e + 32); n_act = ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
-        const bool active = in_stream && (unsigned)s_in < (unsigned)S && (unsigned)a < (unsigned)A;
-        if (in_stream && !active) bad++;
+        const bool active = in_stream;
         // inactive lanes get a private key so they match nobody; their table index is clamped to 0
         const int s = active ? s_in : (0x40000000 | lane);
         const int key = active ? s_in * A + a : (0x40000000 | lane);
         const int sx = active ? s_in : 0;
-        const int kx = active ? key : 0;
+        const int kx = active ? s_in * A + a : 0;
 
         // ---- phase 1: running moments of every row's cell, in time order -------------------
         const unsigned mk = __match_any_sync(FULL_MASK, key);
@@ -369,11 +377,14 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             if (in_stream) st_stream(oall + e, (OT)ov);
         }
         if (in_stream) {
-            st_stream(oval + e, active ? (OT)m_out : (OT)CUDART_NAN);
+            st_stream(oval + e, (OT)m_out);
             st_stream(oact + e, g_out);
         }
         __syncwarp();   // table writes of this batch are ordered before the next batch's reads
-    }
+    };
+    unsigned k = lane;
+    for (; k - lane + 32 <= n_steps; k += 32) batch(std::false_type{}, k);
+    if (k - lane < n_steps) batch(std::true_type{}, k);
     for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)sargs[s].actstep;
     if (p.act_hist != nullptr) {
         // rows since the last argmax change of each state carry the state's current argmax
