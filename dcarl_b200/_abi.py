@@ -66,6 +66,8 @@ SIGNATURES = {
     "dcarl_box_moments_ws": (_sz, [_i32, _i32, _i32]),
     "dcarl_box_moments": (_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
     "dcarl_box_select": (_int, [_vp, _i32, _i32, C.POINTER(RlsParams), _vp, _vp, _vp]),
+    "dcarl_add_data_counts": (_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "dcarl_add_data_rows": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _d, _vp, _vp, _vp]),
     "dcarl_rollout_cv": (_int, [_vp, _vp, _i64, _i32, _f, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
 }
 

@@ -7,6 +7,7 @@ state_with_action / _calculate_visited_times / _calculate_statistics_index), sam
 (RLS.py:61-69) is replaced by a float32 device copy of the buffer that one kernel pass scans for
 all candidate actions at once (csrc/box.cu); `state_index.dat/.idx` are neither read nor written.
 """
+import ctypes as C
 import os
 import os.path as osp
 import random
@@ -36,6 +37,10 @@ class BoxBuffer:
         self._state = torch.empty((capacity, self.D + 1), dtype=torch.float32, device=self.device)
         self._ret = torch.empty((capacity,), dtype=torch.float32, device=self.device)
         self._ws = None
+        self._index_dim = None      # see build_index(): rows [0, _index_rows) are sorted by this dim
+        self._index_rows = 0
+        self._index_col = None
+        self.last_scanned_rows = 0
 
     def __len__(self):
         return self.M
@@ -55,30 +60,133 @@ class BoxBuffer:
         m = s.shape[0]
         if r.numel() != m:
             raise ValueError("one return per stored state expected")
-        if self.M + m > self._state.shape[0]:
-            cap = max(2 * self._state.shape[0], self.M + m)
+        self.reserve(self.M + m)
+        self._state[self.M:self.M + m] = s
+        self._ret[self.M:self.M + m] = r
+        self.M += m
+
+    def append_episodes(self, obs, action, rew, done, ep_offsets, gamma=0.95, lag=10):
+        """Batched RLS.add_data (RLS.py:185-215) for many concurrent transition streams: builds the
+        lagged / terminal-discounted returns on the device and appends the recorded transitions
+        (stream-major, time order).  obs [N, D], action/rew/done [N], ep_offsets [E+1] (stream e owns
+        transitions ep_offsets[e]:ep_offsets[e+1]).  Returns the number of rows appended."""
+        L = _abi.lib()
+        o = _dev.as_device(obs, torch.float32, self.device).reshape(-1, self.D).contiguous()
+        a = _dev.as_device(action, torch.int32, self.device).reshape(-1)
+        r = _dev.as_device(rew, torch.float32, self.device).reshape(-1)
+        if isinstance(done, torch.Tensor):
+            d = done.to(device=self.device, dtype=torch.uint8).reshape(-1).contiguous()
+        else:
+            d = torch.from_numpy(np.ascontiguousarray(np.asarray(done).astype(np.uint8)).reshape(-1)).to(self.device)
+        off = _dev.as_device(ep_offsets, torch.int64, self.device).reshape(-1)
+        N, E = o.shape[0], off.numel() - 1
+        if not (a.numel() == r.numel() == d.numel() == N):
+            raise ValueError("obs, action, rew and done must describe the same N transitions")
+        if E <= 0 or N == 0:
+            return 0
+        sh = _dev.stream_handle()
+        counts = torch.empty(E, dtype=torch.int64, device=self.device)
+        _abi.check(L.dcarl_add_data_counts(_dev.ptr(r), _dev.ptr(d), _dev.ptr(off), E, lag, _dev.ptr(counts), sh))
+        row_off = torch.zeros(E + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=row_off[1:])
+        total = int(row_off[-1].item())
+        if total == 0:
+            return 0
+        ep_of_row = torch.repeat_interleave(torch.arange(E, dtype=torch.int32, device=self.device), off[1:] - off[:-1])
+        self.reserve(self.M + total)
+        st_out = self._state[self.M:self.M + total]
+        rt_out = self._ret[self.M:self.M + total]
+        _abi.check(L.dcarl_add_data_rows(_dev.ptr(o), _dev.ptr(a), _dev.ptr(r), _dev.ptr(d), _dev.ptr(off),
+                                         _dev.ptr(row_off), _dev.ptr(ep_of_row), N, self.D, lag, float(gamma),
+                                         _dev.ptr(st_out), _dev.ptr(rt_out), sh))
+        self.M += total
+        return total
+
+    def reserve(self, rows):
+        """Grow the device arrays to hold at least `rows` rows (amortised doubling)."""
+        if rows > self._state.shape[0]:
+            cap = max(2 * self._state.shape[0], rows)
             ns = torch.empty((cap, self.D + 1), dtype=torch.float32, device=self.device)
             nr = torch.empty((cap,), dtype=torch.float32, device=self.device)
             ns[:self.M] = self._state[:self.M]
             nr[:self.M] = self._ret[:self.M]
             self._state, self._ret = ns, nr
-        self._state[self.M:self.M + m] = s
-        self._ret[self.M:self.M + m] = r
-        self.M += m
 
-    def moments(self, queries, n_actions, out=None, stream=None):
-        """queries float64 [Q, D] (numpy or CUDA tensor) -> CUDA float64 [Q, n_actions, 3] = (n, sum R, sum R^2)."""
-        q = _dev.as_device(queries, torch.float64, self.device).reshape(-1, self.D).contiguous()
-        Q = q.shape[0]
+    def _scan(self, row_lo, row_hi, q, n_actions, out, stream=None):
+        """One kernel pass over rows [row_lo, row_hi) (row_lo a multiple of 4: 16-byte aligned tiles)."""
         L = _abi.lib()
+        Q = q.shape[0]
         need = L.dcarl_box_moments_ws(Q, self.D, n_actions)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
+        sp = C.c_void_p(self._state.data_ptr() + row_lo * (self.D + 1) * 4)
+        rp = C.c_void_p(self._ret.data_ptr() + row_lo * 4)
+        _abi.check(L.dcarl_box_moments(sp, rp, row_hi - row_lo, self.D, _dev.ptr(self.dist), _dev.ptr(q), Q,
+                                       n_actions, _dev.ptr(out), _dev.ptr(self._ws), self._ws.numel(),
+                                       _dev.stream_handle(stream)))
+        self.last_scanned_rows += (row_hi - row_lo) if Q else 0
+
+    def moments(self, queries, n_actions, out=None, stream=None):
+        """queries float64 [Q, D] (numpy or CUDA tensor) -> CUDA float64 [Q, n_actions, 3] = (n, sum R, sum R^2).
+        One streaming pass over the whole buffer, whatever Q is."""
+        q = _dev.as_device(queries, torch.float64, self.device).reshape(-1, self.D).contiguous()
+        if out is None:
+            out = torch.empty((q.shape[0], n_actions, 3), dtype=torch.float64, device=self.device)
+        self.last_scanned_rows = 0
+        self._scan(0, self.M, q, n_actions, out, stream)
+        return out
+
+    # ---- on-device index (SURVEY "next" row f1) ------------------------------------------------
+    def build_index(self, dim=None):
+        """Sort the stored rows by one observation dimension so that a query only has to scan the
+        contiguous run of rows whose value in that dimension lies within the box half-width of the
+        query (every other row fails the closed-box test in that dimension anyway).  The scan kernel
+        and its exact test are unchanged; only its row range shrinks.  `dim` defaults to the
+        dimension with the smallest box-width / data-spread ratio.  Rows appended later form an
+        unsorted tail that is scanned in full until the index is rebuilt."""
+        if self.M == 0:
+            return None
+        st = self.state
+        if dim is None:
+            qs = torch.quantile(st[:: max(1, self.M // 200000), :self.D].double(),
+                                torch.tensor([0.01, 0.99], dtype=torch.float64, device=self.device), dim=0)
+            spread = (qs[1] - qs[0]).clamp_min(1e-12)
+            dim = int(torch.argmin(2 * self.dist[:self.D] / spread).item())
+        n_sorted = (self.M // 4) * 4          # keeps the tail 16-byte aligned; <= 3 rows stay in the tail
+        order = torch.argsort(st[:n_sorted, dim], stable=True)
+        self._state[:n_sorted] = st[:n_sorted][order]
+        self._ret[:n_sorted] = self.ret[:n_sorted][order]
+        self._index_dim, self._index_rows = int(dim), n_sorted
+        self._index_col = self._state[:n_sorted, dim].contiguous()
+        return self._index_dim
+
+    def moments_indexed(self, queries, n_actions, out=None):
+        """Same result as ``moments`` (counts identical, sums up to float64 addition order), scanning
+        per query only the index range that can match plus the unsorted tail.  Meant for few queries
+        (one launch per query); ``last_scanned_rows`` reports the rows actually read."""
+        if self._index_dim is None:
+            return self.moments(queries, n_actions, out)
+        q = _dev.as_device(queries, torch.float64, self.device).reshape(-1, self.D).contiguous()
+        Q = q.shape[0]
         if out is None:
             out = torch.empty((Q, n_actions, 3), dtype=torch.float64, device=self.device)
-        _abi.check(L.dcarl_box_moments(_dev.ptr(self._state), _dev.ptr(self._ret), self.M, self.D,
-                                       _dev.ptr(self.dist), _dev.ptr(q), Q, n_actions, _dev.ptr(out),
-                                       _dev.ptr(self._ws), self._ws.numel(), _dev.stream_handle(stream)))
+        d = self._index_dim
+        w = self.dist[d]
+        # float32 bracket, widened by 2 ulp: a prefilter only, the kernel applies the exact test
+        lo = torch.nextafter(torch.nextafter((q[:, d] - w).float(), torch.tensor(-float("inf"), device=self.device)),
+                             torch.tensor(-float("inf"), device=self.device))
+        hi = torch.nextafter(torch.nextafter((q[:, d] + w).float(), torch.tensor(float("inf"), device=self.device)),
+                             torch.tensor(float("inf"), device=self.device))
+        r0 = torch.searchsorted(self._index_col, lo, right=False).cpu().tolist()
+        r1 = torch.searchsorted(self._index_col, hi, right=True).cpu().tolist()
+        self.last_scanned_rows = 0
+        tmp = torch.empty((1, n_actions, 3), dtype=torch.float64, device=self.device)
+        for i in range(Q):
+            a, b = (r0[i] // 4) * 4, r1[i]
+            self._scan(a, max(a, b), q[i:i + 1], n_actions, out[i:i + 1])
+            if self.M > self._index_rows:                      # unsorted tail (appended after build_index)
+                self._scan(self._index_rows, self.M, q[i:i + 1], n_actions, tmp)
+                out[i:i + 1] += tmp
         return out
 
     def select(self, moments, rls_params=None, stream=None, out=None):
@@ -102,8 +210,11 @@ class BoxBuffer:
         return _BoxQueryGraph(self, int(Q), int(n_actions), rls_params or _abi.RlsParams())
 
     def query(self, obs, n_actions=8, rls_params=None):
-        """obs [D] or [Q, D] -> host (n [Q, A], mean [Q, A], var [Q, A], action [Q])."""
-        mom = self.moments(np.asarray(obs, np.float64).reshape(-1, self.D), n_actions)
+        """obs [D] or [Q, D] -> host (n [Q, A], mean [Q, A], var [Q, A], action [Q]).  Uses the index
+        (if built) for up to 8 queries, the single full pass otherwise."""
+        q = np.asarray(obs, np.float64).reshape(-1, self.D)
+        use_index = self._index_dim is not None and len(q) <= 8
+        mom = self.moments_indexed(q, n_actions) if use_index else self.moments(q, n_actions)
         mv, pick = self.select(mom, rls_params)
         mom_h, mv_h = mom.cpu().numpy(), mv.cpu().numpy()
         return mom_h[:, :, 0], mv_h[:, :, 0], mv_h[:, :, 1], pick.cpu().numpy()
@@ -184,6 +295,7 @@ class RLS(object):
                 raise ValueError("visited_state.txt and visited_value.txt disagree on the row count")
             if len(states):
                 self.visited_state_tree.append(states, np.asarray(self.visited_state_value)[:, 1])
+                self.visited_state_tree.build_index()      # stands in for the rtree: queries scan one sorted run
         self.visited_state_outfile = open("visited_state.txt", "a")
         self.visited_state_format = " ".join(("%f",) * (self.obs_dimension + 1)) + "\n"
         self.visited_value_outfile = open("visited_value.txt", "a")

@@ -154,6 +154,24 @@ int dcarl_box_select(const double *moments, int32_t Q, int32_t n_actions,
                      const dcarl_rls_params *p /* host */, double *out_mean_var,
                      int32_t *out_action, dcarl_stream_t stream);
 
+/* ---- a13 / "next" row f2: batched RLS.add_data return construction, RLS:185-215 ----------------
+ * E concurrent transition streams, concatenated: stream e owns transitions
+ * [ep_offsets[e], ep_offsets[e+1]) of obs (float32 [N, D]), action (int32 [N]), rew (float32 [N]),
+ * done (uint8 [N]).  A transition is recorded with its own reward once `lag` (10) newer ones have
+ * arrived; a transition with done != 0 flushes everything still queued with its reward times
+ * gamma^distance; transitions still queued when the stream stops are not recorded.  Recorded
+ * transitions of a stream are a prefix of it.
+ *   dcarl_add_data_counts: out_counts[e] = number of recorded transitions of stream e.
+ *   dcarl_add_data_rows:   with row_offsets = exclusive scan of the counts and ep_of_row[i] = the
+ *     stream of transition i, writes buffer rows out_state (float32 [rows, D+1] = obs (+) action,
+ *     RLS:91-93) and out_ret (float32 [rows]) in stream-major, time order. */
+int dcarl_add_data_counts(const float *rew, const uint8_t *done, const int64_t *ep_offsets, int64_t E,
+                          int32_t lag, int64_t *out_counts, dcarl_stream_t stream);
+int dcarl_add_data_rows(const float *obs, const int32_t *action, const float *rew, const uint8_t *done,
+                        const int64_t *ep_offsets, const int64_t *row_offsets, const int32_t *ep_of_row,
+                        int64_t N, int32_t D, int32_t lag, double gamma, float *out_state, float *out_ret,
+                        dcarl_stream_t stream);
+
 /* ---- a14: constant-velocity rollout surrogate (CARLA itself is external) -----
  * state0 float32 [n, 20] = ego + 3 objects x [x, y, vx, vy, yaw]; the ego velocity is scaled
  * by speed_scale[action]; every step advances all four bodies by v*dt, a collision

@@ -201,3 +201,59 @@ def test_query_graph_replay_matches_the_plain_path_and_tracks_appends():
         assert np.array_equal(n, ref[:, :, 0])
         if upto == half:
             buf.append(vs[half:], ret[half:])          # the next call must re-capture with the new row count
+
+
+def test_batched_add_data_matches_the_reference_deque():
+    """SURVEY next-row f2: many transition streams at once against the literal deque restatement
+    (RLS.py:185-215), including streams with no done, several dones, and fewer than 10 steps."""
+    rng = np.random.default_rng(2)
+    lens = [0, 1, 9, 10, 11, 25, 40, 200] + rng.integers(1, 120, 40).tolist()
+    obs, act, rew, done, offs = [], [], [], [], [0]
+    want_state, want_ret = [], []
+    for e, T in enumerate(lens):
+        o = rng.normal(0, 5, (T, 20)).astype(np.float32)
+        a = rng.integers(0, 8, T).astype(np.int32)
+        r = np.where(rng.random(T) < 0.2, -rng.random(T), 0.0).astype(np.float32)
+        d = rng.random(T) < (0.0 if e % 5 == 0 else 0.03)
+        if T and e % 3 == 1:
+            d[-1] = True
+        rec = pyref.add_data_returns(r.astype(np.float64).tolist(), d.tolist())
+        assert [t for t, _ in rec] == list(range(len(rec)))              # recorded rows are a prefix, in time order
+        for t, R in rec:
+            want_state.append(np.append(o[t], np.float32(a[t])))
+            want_ret.append(np.float32(R))
+        obs.append(o); act.append(a); rew.append(r); done.append(d); offs.append(offs[-1] + T)
+    buf = dc.BoxBuffer(20, capacity=8)
+    n = buf.append_episodes(np.concatenate(obs), np.concatenate(act), np.concatenate(rew), np.concatenate(done), offs)
+    assert n == len(want_ret) == len(buf)
+    assert np.array_equal(buf.state.cpu().numpy(), np.asarray(want_state, np.float32))
+    assert np.allclose(buf.ret.cpu().numpy(), np.asarray(want_ret, np.float32), rtol=2e-7, atol=0)
+    # appending again lands after the first block
+    m = buf.append_episodes(obs[7], act[7], rew[7], done[7], [0, lens[7]])
+    assert len(buf) == n + m and m >= lens[7] - 10
+
+
+def test_sorted_index_gives_the_same_answers_on_a_fraction_of_the_rows(golden):
+    """SURVEY next-row f1: the on-device index only narrows the scanned row range."""
+    g = golden("rls_box")
+    vs, vv, dr = g["visited_state"], g["visited_value"], g["driving_record"]
+    plain = dc.BoxBuffer(20)
+    plain.append(vs, vv[:, 1])
+    idx = dc.BoxBuffer(20)
+    idx.append(vs[:-5001], vv[:-5001, 1])
+    dim = idx.build_index()
+    assert 0 <= dim < 20
+    idx.append(vs[-5001:], vv[-5001:, 1])                      # unsorted tail, odd length
+    for lo in range(0, 107, 8):
+        q = dr[lo:lo + 8, :20]
+        n0, m0, v0, p0 = plain.query(q, 8)
+        n1, m1, v1, p1 = idx.query(q, 8)
+        assert np.array_equal(n0, n1) and np.array_equal(p0, p1)
+        assert np.abs(m0 - m1).max() < 1e-12 and np.abs(v0 - v1).max() < 1e-12
+        assert idx.last_scanned_rows < 0.8 * len(q) * len(vs)
+    assert np.array_equal(idx.query(dr[:, :20], 8)[0][:, 0], dr[:, 23])     # > 8 queries: the single full pass
+    for d in (0, 5, 17):                                       # any dimension is a valid sort key
+        b = dc.BoxBuffer(20)
+        b.append(vs, vv[:, 1])
+        assert b.build_index(d) == d
+        assert np.array_equal(b.query(dr[40:44, :20], 8)[0], plain.query(dr[40:44, :20], 8)[0])
