@@ -18,6 +18,7 @@ from .sampling import (Data_Generation, add_an_act_data, generate, random_state_
                        random_state_norm, sample_returns, sample_returns_philox)
 from .rls import RLS, BoxBuffer, VISITED_STATE_DIST  # noqa: F401
 from .rollout import rollout_cv  # noqa: F401
+from .io import load_rls_buffer, load_sim_data, save_rls_buffer  # noqa: F401
 from . import dist  # noqa: F401
 
 __version__ = "0.1.0"
