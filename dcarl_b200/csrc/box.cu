@@ -165,14 +165,13 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
             const float *l = slo + q * D, *h = shi + q * D;
             bool ok = in_buf;
             if (DT > 0) {
-                // four dims at a time; most (row, query) pairs are rejected by the first group, so with
-                // many queries the warp leaves early instead of paying 2*D compares per pair
+                constexpr int kHead = DT < 4 ? DT : 4;
 #pragma unroll
-                for (int d0 = 0; d0 < DT; d0 += 4) {
+                for (int d = 0; d < kHead; ++d) ok = ok && (xr[d] >= l[d]) && (xr[d] <= h[d]);
+                // with many queries most (row, query) pairs die on the first dims: leave before the rest
+                if (p.Q > 1 && !__any_sync(FULL_MASK, ok)) continue;
 #pragma unroll
-                    for (int d = d0; d < d0 + 4 && d < DT; ++d) ok = ok && (xr[d] >= l[d]) && (xr[d] <= h[d]);
-                    if (p.Q > 1 && d0 + 4 < DT && !__any_sync(FULL_MASK, ok)) break;
-                }
+                for (int d = kHead; d < DT; ++d) ok = ok && (xr[d] >= l[d]) && (xr[d] <= h[d]);
             } else {
                 for (int d = 0; d < D; ++d) { const float v = x[d]; ok = ok && (v >= l[d]) && (v <= h[d]); }
             }
