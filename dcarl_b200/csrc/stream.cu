@@ -244,13 +244,15 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         const bool active = in_stream;
         // inactive lanes get a private key so they match nobody; their table index is clamped to 0
         const int s = active ? s_in : (0x40000000 | lane);
-        const int key = active ? s_in * A + a : (0x40000000 | lane);
         const int sx = active ? s_in : 0;
         const int kx = active ? s_in * A + a : 0;
 
         // ---- phase 1: running moments of every row's cell, in time order -------------------
-        const unsigned mk = __match_any_sync(FULL_MASK, key);
+        // peers of the same state / the same cell.  match.any takes about one round per distinct
+        // value in the warp, so the cell mask is the AND of a state match and an action match
+        // (~13 + ~11 distinct values) rather than a match on the cell key (~28).
         const unsigned ms = __match_any_sync(FULL_MASK, s);
+        const unsigned mk = ms & __match_any_sync(FULL_MASK, a);
         Cell *cell = cells + kx;
         double acc1 = cell->s1, acc2 = cell->s2;
         const unsigned n0 = cnt[kx];
