@@ -349,8 +349,10 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         }
 
         // ---- activation step (ST1:98-99): first row of a state whose argmax is not the rule action
-        const unsigned need = __ballot_sync(FULL_MASK, active && ast == -1 && g_out != rule) & ms;
-        if (__any_sync(FULL_MASK, need != 0)) {   // rare: once per state
+        unsigned need = 0;
+        const bool any_need = __any_sync(FULL_MASK, active && ast == -1 && g_out != rule);   // warp-uniform
+        if (any_need) {   // rare: once per state
+            need = __ballot_sync(FULL_MASK, active && ast == -1 && g_out != rule) & ms;
             __syncwarp();
             if (need && lane == __ffs(need) - 1) {
                 unsigned csum = 0;
@@ -361,14 +363,20 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         if (OVERALL) {                                                            // ST2:99-105
             // contribution of the row's state after the row, minus before it; prefix-summed over the batch
             const bool act_before = ast != -1;
-            const bool act_now = active && (act_before || (need & le) != 0);
-            const double c_k = act_now ? m_out + bonus : 0.0;
             const unsigned prev = ms & lt;
             const int pl = prev ? (31 - __clz(prev)) : lane;
-            const double c_prev_lane = shfl_f64(c_k, pl);
-            const double c_start = act_before ? smax0 + bonus : 0.0;
-            double d = c_k - (prev ? c_prev_lane : c_start);
-            if (!active) d = 0.0;
+            double d;
+            if (!any_need) {
+                // no state activates in this batch (warp-uniform branch): the bonus cancels in the difference
+                const double m_prev_lane = shfl_f64(m_out, pl);
+                d = (active && act_before) ? m_out - (prev ? m_prev_lane : smax0) : 0.0;
+            } else {
+                const bool act_now = active && (act_before || (need & le) != 0);
+                const double c_k = act_now ? m_out + bonus : 0.0;
+                const double c_prev_lane = shfl_f64(c_k, pl);
+                const double c_start = act_before ? smax0 + bonus : 0.0;
+                d = active ? c_k - (prev ? c_prev_lane : c_start) : 0.0;
+            }
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const double o = __shfl_up_sync(FULL_MASK, d, off);
