@@ -286,9 +286,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         // ---- phase 2: per-row (max, argmax) of the row's state ----------------------------
         // Round 1 assumes nobody's argmax moves; a row that might move it is replayed exactly and
         // the rows after it retry (rare).
-        const double smax0 = h.smax;   // the state's max when the batch began (for overall_value)
         const int ast = ga.actstep;
-        double m_out = 0.0;
+        double m_out = 0.0, mprev_out = 0.0;   // the state's max just after / just before this row
         int g_out = -1;
         unsigned pend = __ballot_sync(FULL_MASK, active);
         bool mine = active;
@@ -297,10 +296,11 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const int c_g = ga.sarg;
             const bool T = mine && upd && a == c_g;        // row refreshes the argmax cell of its state
             const unsigned tm = __ballot_sync(FULL_MASK, T);
-            const unsigned cand = tm & ms & le;
-            const int jl = cand ? (31 - __clz(cand)) : lane;
-            const double vj = shfl_f64(v, jl);
-            const double m_k = cand ? vj : c_ms0;
+            const unsigned cand = tm & ms & lt;            // earlier argmax-cell rows of my state
+            const int jp = cand ? (31 - __clz(cand)) : lane;
+            const double vp = shfl_f64(v, jp);
+            const double m_prev = cand ? vp : c_ms0;       // the state's max just before this row ...
+            const double m_k = T ? v : m_prev;             // ... and just after it (if nobody's argmax moves)
             // a row keeps the argmax if it refreshes the argmax cell to above the runner-up bound, or
             // another cell to at most that bound (and below the running max)
             bool fail = mine && upd && (T ? !(v > c_ub) : !(v <= c_ub && v < m_k));
@@ -313,7 +313,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const unsigned fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;   // pending rows before the first doubtful one
             __syncwarp();   // every lane has consumed its state record before a peer overwrites it
             if (mine && (fin & bit)) {
-                g_out = c_g; m_out = m_k;
+                g_out = c_g; m_out = m_k; mprev_out = m_prev;
                 if (upd && (mk & fin & gt) == 0) cell->val = v;
                 if ((ms & fin & gt) == 0) sh->smax = m_k;
                 if (lift) sh->sub2 = runner_up_bound(v, m_k);
@@ -337,7 +337,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 if (lane == j) { hist[old_g] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1; }
             }
             if (lane == j) {
-                g_out = arg; m_out = mx;
+                g_out = arg; m_out = mx; mprev_out = m_prev;
                 sh->smax = mx; sh->sub2 = runner_up_bound(second, mx); sa->sarg = arg;
             }
             __syncwarp();
@@ -363,19 +363,13 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         if (OVERALL) {                                                            // ST2:99-105
             // contribution of the row's state after the row, minus before it; prefix-summed over the batch
             const bool act_before = ast != -1;
-            const unsigned prev = ms & lt;
-            const int pl = prev ? (31 - __clz(prev)) : lane;
             double d;
             if (!any_need) {
                 // no state activates in this batch (warp-uniform branch): the bonus cancels in the difference
-                const double m_prev_lane = shfl_f64(m_out, pl);
-                d = (active && act_before) ? m_out - (prev ? m_prev_lane : smax0) : 0.0;
+                d = (active && act_before) ? m_out - mprev_out : 0.0;
             } else {
-                const bool act_now = active && (act_before || (need & le) != 0);
-                const double c_k = act_now ? m_out + bonus : 0.0;
-                const double c_prev_lane = shfl_f64(c_k, pl);
-                const double c_start = act_before ? smax0 + bonus : 0.0;
-                d = active ? c_k - (prev ? c_prev_lane : c_start) : 0.0;
+                const bool act_now = act_before || (need & le) != 0, act_prev = act_before || (need & lt) != 0;
+                d = active ? (act_now ? m_out + bonus : 0.0) - (act_prev ? mprev_out + bonus : 0.0) : 0.0;
             }
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
