@@ -358,33 +358,29 @@ class RLS(object):
         return np.array(pick)
 
     # RLS.py:161-181 — the trailing arguments of the reference signatures are accepted and unused
+    def _nmv(self, point):
+        """(n, mean, var) for one query point obs (+) action (RLS.py:91-93)."""
+        point = np.asarray(point, np.float64).reshape(-1)
+        a = float(point[self.obs_dimension])
+        ai = int(round(a))
+        if ai != a or ai < 0:
+            raise ValueError("the action coordinate of a query must be a non-negative integer "
+                             "(the reference only ever queries integer candidate actions)")
+        if ai < self.n_actions:
+            ns, means, vars_, _ = self._stats(point)
+        else:                                        # beyond the candidate set: one wider scan, not cached
+            ns, means, vars_, _ = self.visited_state_tree.query(point[:self.obs_dimension], ai + 1)
+            ns, means, vars_ = ns[0], means[0], vars_[0]
+        return int(ns[ai]), float(means[ai]), float(vars_[ai])
+
     def _calculate_visited_times(self, obs, visited_state_tree=None):
-        obs = np.asarray(obs, np.float64).reshape(-1)
-        a = obs[self.obs_dimension]
-        n, _, _, _ = self._stats(obs)
-        ai = int(round(float(a)))
-        if ai != a or not (0 <= ai < self.n_actions):
-            return self._scan_single(obs)[0]
-        return int(n[ai])
+        return self._nmv(obs)[0]
 
     def _calculate_statistics_index(self, obs, visited_state_value=None, visited_state_tree=None):
-        obs = np.asarray(obs, np.float64).reshape(-1)
-        a = obs[self.obs_dimension]
-        ai = int(round(float(a)))
-        if ai != a or not (0 <= ai < self.n_actions):
-            n, mean, var = self._scan_single(obs)
-        else:
-            ns, means, vars_, _ = self._stats(obs)
-            n, mean, var = int(ns[ai]), float(means[ai]), float(vars_[ai])
+        n, mean, var = self._nmv(obs)
         if n == 0:
-            return -1, -1, -1
+            return -1, -1, -1                        # RLS.py:169-170
         return mean, var, np.sqrt(var)
-
-    def _scan_single(self, point):
-        """A query whose action coordinate is not one of the integer candidates (never happens in
-        the reference's own call sites): scan with that action as candidate 0 by shifting the
-        action axis."""
-        raise ValueError("query action must be an integer in [0, n_actions)")
 
     # RLS.py:185-241
     def add_data(self, obs, action, rew, new_obs, done):

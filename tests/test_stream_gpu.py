@@ -56,6 +56,8 @@ SHAPES = [
     (6, 800, 4, 6, {"n_thres": 0}),              # refresh from the first sample
     (6, 800, 4, 6, {"prior_other": 100.0}),      # priors tie with the rule action
     (4, 600, 2, 3, {"alpha": 0.2, "scale": 40.0, "cap": 60.0, "activation_bonus": 2.5}),
+    (3, 4000, 30, 256, {}),                      # config-4-sized action set: 7680 cells, one instance per CTA
+    (2, 300, 1, 1, {}),                          # a single cell
 ]
 
 
