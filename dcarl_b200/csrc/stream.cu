@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(kRowsMaxWarps * 32, 4)
 k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0: tells the compiler the warp index (hence `inst` and every loop bound)
+    // is warp-uniform, so the warp-synchronous intrinsics below need no divergence fallbacks
+    const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
 
     const long long inst = (long long)blockIdx.x * warps_per_cta + warp;
     if (inst >= p.n_inst) return;
@@ -403,6 +405,363 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, (unsigned long long)bad);
 }
 
+// ---- software-pipelined row kernel ---------------------------------------------------------
+// Same tables, same per-row logic and the same results as k_stream_rows; the loop is skewed by
+// one batch.  The moment stage of batch b+1 (row loads, peer matching, running moments, bound)
+// touches only {cnt, s1, s2}; the selector stage of batch b (argmax bookkeeping, overall_value
+// scan, output stores) touches only {val, state records}.  Placing the two in the same
+// straight-line region gives every warp two independent dependency chains, which is what the
+// 7-warps-per-scheduler residency of config 2 lacks.  The first selector round is peeled out
+// of its retry loop so that it shares a basic block with the next batch's moment loads.
+// float32 outputs scan the in-batch overall_value deltas in float32 (the running total stays
+// float64; activation jumps, rare, are added in float64).
+// Lanes of the same state (ms) and of the same cell (mk).  match.any takes about one round per
+// distinct value in the warp, so the cell mask is the AND of a state match and an action match
+// rather than a match on the cell key.  BALLOT: the same masks from one ballot per key bit
+// (nb_s + nb_a ballots; short dependency chain, more instructions).
+template <bool BALLOT>
+__device__ __forceinline__ void peer_masks(int s, int a, bool active, unsigned &ms, unsigned &mk) {
+    if (!BALLOT) {
+        ms = __match_any_sync(FULL_MASK, s);
+        mk = ms & __match_any_sync(FULL_MASK, a);
+    } else {
+        // experiment build: 5 state bits, 4 action bits (S <= 32, A <= 16; checked by the host)
+        unsigned m = __ballot_sync(FULL_MASK, active);
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const bool on = (s >> b) & 1;
+            const unsigned bal = __ballot_sync(FULL_MASK, on);
+            m &= on ? bal : ~bal;
+        }
+        ms = active ? m : (1u << lane_id());
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const bool on = (a >> b) & 1;
+            const unsigned bal = __ballot_sync(FULL_MASK, on);
+            m &= on ? bal : ~bal;
+        }
+        mk = active ? m : (1u << lane_id());
+    }
+}
+
+template <typename RT, typename OT, bool OVERALL, int FLAGS>
+__global__ void __launch_bounds__(kRowsMaxWarps * 32, 4)
+k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned warp_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id();
+    // broadcast from lane 0: tells the compiler the warp index (hence `inst` and every loop bound)
+    // is warp-uniform, so the warp-synchronous intrinsics below need no divergence fallbacks
+    const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
+
+    const long long inst = (long long)blockIdx.x * warps_per_cta + warp;
+    if (inst >= p.n_inst) return;
+
+    const int S = p.S, A = p.A, ncell = S * A;
+    StateHot *hot = reinterpret_cast<StateHot *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
+    StateArg *sargs = reinterpret_cast<StateArg *>(hot + S);
+    Cell *cells = reinterpret_cast<Cell *>(sargs + S);
+    unsigned *cnt = reinterpret_cast<unsigned *>(cells + ncell);
+    int *flushpt = reinterpret_cast<int *>(cnt + ncell);
+    unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
+
+    for (int c = lane; c < ncell; c += 32) {
+        cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
+        cells[c].val = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
+    }
+    for (int a = lane; a < A; a += 32) hist[a] = 0u;
+    __syncwarp();
+    {
+        double m0, sec0; int g0;
+        warp_top2(&cells[0].val, 3, A, m0, g0, sec0);
+        StateHot h0;
+        h0.smax = m0; h0.sub2 = runner_up_bound(sec0, m0);
+        StateArg a0;
+        a0.sarg = g0; a0.actstep = -1;                                          // ST1:58
+        for (int s = lane; s < S; s += 32) { hot[s] = h0; sargs[s] = a0; flushpt[s] = 0; }
+    }
+    __syncwarp();
+
+    const unsigned bit = 1u << lane;
+    const unsigned lt = bit - 1u, le = lt | bit, gt = ~le;
+    const unsigned n_steps = p.n_steps;
+    const double c_h = p.c_h, cap = p.cap, bonus = p.bonus;
+    const int rule = p.rule_act;
+    const unsigned n_thres = (unsigned)p.n_thres;
+    constexpr bool BALLOT_PEERS = (FLAGS & 1) != 0;
+    constexpr bool SCAN_F32 = std::is_same<OT, float>::value && (FLAGS & 2) == 0;
+
+    const int *__restrict__ gidx = p.idx;
+    const int *__restrict__ gact = p.act;
+    const RT *__restrict__ gR = reinterpret_cast<const RT *>(p.R);
+    OT *__restrict__ oval = reinterpret_cast<OT *>(p.out_value);
+    int *__restrict__ oact = p.out_act;
+    OT *__restrict__ oall = reinterpret_cast<OT *>(p.out_overall);
+    const unsigned ebase = (unsigned)inst * n_steps + lane;
+
+    double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
+    unsigned bad = 0;     // lane-local count of out-of-range rows
+
+    int n_idx = 0, n_act = 0;
+    RT n_R = RT(0);
+    if ((unsigned)lane < n_steps) { n_idx = ld_stream(gidx + ebase); n_act = ld_stream(gact + ebase); n_R = ld_stream(gR + ebase); }
+
+    struct Rows {      // a batch after its moment stage
+        int s, sx, a, kx;
+        unsigned ms, mk, n;
+        double v;
+        bool active;
+    };
+    struct Mom {       // moment stage in flight
+        double acc1, acc2;
+        unsigned earlier;   // earlier lanes of the same cell, oldest first
+        RT rin, r1, r2;     // own return and those of the two oldest earlier peers
+    };
+    struct Sel {       // selector stage results
+        double m_out, mprev_out;
+        int g_out, ast;
+        unsigned need;
+        bool any_need;
+    };
+
+    // ---- moment stage, part a: consume the prefetched rows, request the batch after, find the
+    // peers, load the cell moments, fetch the returns of the two oldest in-batch peers.  Only
+    // issues work: nothing here waits on a shuffle or a shared-memory load.
+    auto p1a = [&](auto tail_tag, const unsigned k, Rows &r, Mom &m) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const bool in_stream = TAIL ? (k < n_steps) : true;
+        const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
+        const int a = (int)min((unsigned)n_act, (unsigned)(A - 1));
+        if (in_stream && (s_in != n_idx || a != n_act)) bad++;
+        m.rin = n_R;
+        const unsigned e = ebase + (k - lane);
+        if (k + 32 < n_steps) { n_idx = ld_stream(gidx + e + 32); n_act = ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
+        r.active = in_stream;
+        r.s = in_stream ? s_in : (0x40000000 | lane);
+        r.sx = in_stream ? s_in : 0;
+        r.a = a;
+        r.kx = in_stream ? s_in * A + a : 0;
+        peer_masks<BALLOT_PEERS>(r.s, a, in_stream, r.ms, r.mk);
+        const Cell *cell = cells + r.kx;
+        m.acc1 = cell->s1; m.acc2 = cell->s2;
+        m.earlier = r.mk & lt;
+        r.n = cnt[r.kx] + __popc(m.earlier) + 1u;
+        const unsigned e1 = m.earlier & (m.earlier - 1);
+        m.r1 = __shfl_sync(FULL_MASK, m.rin, m.earlier ? (__ffs(m.earlier) - 1) : lane);
+        m.r2 = __shfl_sync(FULL_MASK, m.rin, e1 ? (__ffs(e1) - 1) : lane);
+    };
+    // the two oldest peers, then (rare) a loop for more than two earlier peers of the same cell
+    auto p1_peers = [&](Mom &m) {
+        if (m.earlier) {
+            const double x = (double)m.r1; m.acc1 += x; m.acc2 = fma(x, x, m.acc2);
+            m.earlier &= m.earlier - 1;
+            if (m.earlier) {
+                const double y = (double)m.r2; m.acc1 += y; m.acc2 = fma(y, y, m.acc2);
+                m.earlier &= m.earlier - 1;
+            }
+        }
+        while (__any_sync(FULL_MASK, m.earlier != 0)) {
+            const RT rj = __shfl_sync(FULL_MASK, m.rin, m.earlier ? (__ffs(m.earlier) - 1) : lane);
+            if (m.earlier) { const double x = (double)rj; m.acc1 += x; m.acc2 = fma(x, x, m.acc2); m.earlier &= m.earlier - 1; }
+        }
+    };
+    // part b: own return, write-back by the last lane of each cell group, the bound in float64
+    auto p1b = [&](Rows &r, Mom &m) {
+        const double x = (double)m.rin;
+        m.acc1 += x;
+        m.acc2 = fma(x, x, m.acc2);
+        __syncwarp();   // every lane has read its cell
+        if (r.active && (r.mk & gt) == 0) {
+            Cell *cell = cells + r.kx;
+            cnt[r.kx] = r.n; cell->s1 = m.acc1; cell->s2 = m.acc2;
+        }
+        r.v = cell_value(r.n, m.acc1, m.acc2, r.a == rule, c_h, cap);
+    };
+
+    // ---- selector stage: per-row (max, argmax) of the row's state; same logic as k_stream_rows
+    auto p2 = [&](const Rows &r, Sel &o) {
+        const int lane_ = lane;
+        StateHot *sh = hot + r.sx;
+        StateArg *sa = sargs + r.sx;
+        Cell *cell = cells + r.kx;
+        StateHot h = *sh;
+        StateArg ga = *sa;
+        const bool upd = r.active && r.n > n_thres;                               // ST1:86
+        const double v = r.v;
+        const int a = r.a;
+        const unsigned ms = r.ms, mk = r.mk;
+        o.ast = ga.actstep;
+        o.m_out = 0.0; o.mprev_out = 0.0; o.g_out = -1;
+        unsigned pend = __ballot_sync(FULL_MASK, r.active);
+        bool mine = r.active;
+        unsigned fm, fin;
+        double m_prev;
+        auto round = [&]() {
+            const double c_ms0 = h.smax, c_ub = h.sub2;
+            const int c_g = ga.sarg;
+            const bool T = mine && upd && a == c_g;
+            const unsigned tm = __ballot_sync(FULL_MASK, T);
+            const unsigned cand = tm & ms & lt;
+            const int jp = cand ? (31 - __clz(cand)) : lane_;
+            const double vp = shfl_f64(v, jp);
+            m_prev = cand ? vp : c_ms0;
+            const double m_k = T ? v : m_prev;
+            // (bitwise on purpose: all three compares are evaluated, no short-circuit branches)
+            const bool gt_ub = v > c_ub, le_ub = v <= c_ub, lt_mk = v < m_k;
+            const bool doubt = mine & upd & (T ? !gt_ub : !(le_ub & lt_mk));
+            const bool lift = doubt & !T & lt_mk & ((ms & gt) == 0);
+            fm = __ballot_sync(FULL_MASK, doubt & !lift);
+            fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;
+            __syncwarp();
+            const bool done = mine & ((fin & bit) != 0);
+            o.g_out = done ? c_g : o.g_out;
+            o.m_out = done ? m_k : o.m_out;
+            o.mprev_out = done ? m_prev : o.mprev_out;
+            if (done & upd & ((mk & fin & gt) == 0)) cell->val = v;
+            if (done & ((ms & fin & gt) == 0)) sh->smax = m_k;
+            if (done & lift) sh->sub2 = runner_up_bound(v, m_k);
+        };
+        round();
+        if (fm != 0) {
+            for (;;) {
+                // ---- exact replay of the first doubtful row j
+                const int j = __ffs(fm) - 1;
+                __syncwarp();
+                const int sj = __shfl_sync(FULL_MASK, r.s, j);
+                const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
+                if (lane_ == j) cell->val = v;
+                __syncwarp();
+                const int old_g = sargs[sj].sarg;
+                double mx, second; int arg;
+                warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
+                if (arg != old_g) {
+                    unsigned csum = 0;
+                    for (int q = lane_; q < A; q += 32) csum += cnt[sj * A + q];
+                    const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
+                    if (lane_ == j) { hist[old_g] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1; }
+                }
+                if (lane_ == j) {
+                    o.g_out = arg; o.m_out = mx; o.mprev_out = m_prev;
+                    sh->smax = mx; sh->sub2 = runner_up_bound(second, mx); sa->sarg = arg;
+                }
+                __syncwarp();
+                pend &= ~(fin | (1u << j));
+                mine = mine && lane_ > j;
+                if (pend == 0) break;
+                h = *sh;
+                ga = *sa;
+                round();
+                if (fm == 0) break;
+            }
+        }
+        // ---- activation step (ST1:98-99): first row of a state whose argmax is not the rule action
+        o.need = __ballot_sync(FULL_MASK, r.active && o.ast == -1 && o.g_out != rule);
+        o.any_need = o.need != 0;                                                  // warp-uniform
+        o.need &= ms;
+        if (o.any_need) {   // rare: once per state
+            __syncwarp();
+            if (o.need && lane_ == __ffs(o.need) - 1) {
+                unsigned csum = 0;
+                for (int q = 0; q < A; ++q) csum += cnt[r.sx * A + q];
+                sa->actstep = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
+            }
+        }
+    };
+
+    // ---- outputs of a batch: overall_value prefix over the batch (ST2:99-105), stores
+    auto fin_out = [&](auto tail_tag, const unsigned k, const Rows &r, const Sel &o) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const bool in_stream = TAIL ? r.active : true;
+        const unsigned e = ebase + (k - lane);
+        if (in_stream) {
+            st_stream(oval + e, (OT)o.m_out);
+            st_stream(oact + e, o.g_out);
+        }
+        if (OVERALL) {
+            const bool act_before = o.ast != -1;
+            // rows of states that were active before the row: the bonus cancels in after - before
+            const bool act_prev = act_before || (o.need & lt) != 0;
+            const double d = (r.active && act_prev) ? o.m_out - o.mprev_out : 0.0;
+            double pre;
+            if constexpr (SCAN_F32) {
+                float f = (float)d;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float q = __shfl_up_sync(FULL_MASK, f, off);
+                    if (lane >= off) f += q;
+                }
+                pre = (double)f;
+            } else {
+                pre = d;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double q = __shfl_up_sync(FULL_MASK, pre, off);
+                    if (lane >= off) pre += q;
+                }
+            }
+            if (o.any_need) {   // rare: a state activates at this row, its (max + bonus) enters the sum
+                double jmp = (r.active && !act_prev && (o.need & le) != 0) ? o.m_out + bonus : 0.0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double q = __shfl_up_sync(FULL_MASK, jmp, off);
+                    if (lane >= off) jmp += q;
+                }
+                pre += jmp;
+            }
+            const double ov = total + pre;
+            total += shfl_f64(pre, 31);
+            if (in_stream) st_stream(oall + e, (OT)ov);
+        }
+    };
+
+    const unsigned nfull = n_steps >> 5;
+    unsigned k = lane;
+    Rows cur;
+    Mom mom;
+    Sel sel;
+    if (nfull) {
+        p1a(std::false_type{}, k, cur, mom);
+        p1_peers(mom);
+        p1b(cur, mom);
+        __syncwarp();
+        for (unsigned b = 1; b < nfull; ++b) {
+            Rows nxt;
+            p1a(std::false_type{}, k + 32, nxt, mom);   // reads {cnt, s1, s2} only
+            p2(cur, sel);                               // reads/writes {val, state records}; cnt read-only
+            p1_peers(mom);
+            p1b(nxt, mom);                              // writes {cnt, s1, s2}
+            fin_out(std::false_type{}, k, cur, sel);
+            __syncwarp();   // table writes of this iteration are ordered before the next one's reads
+            cur = nxt;
+            k += 32;
+        }
+        p2(cur, sel);
+        fin_out(std::false_type{}, k, cur, sel);
+        __syncwarp();
+        k += 32;
+    }
+    if (k - lane < n_steps) {   // ragged last batch: lanes past the end of the stream are inactive
+        p1a(std::true_type{}, k, cur, mom);
+        p1_peers(mom);
+        p1b(cur, mom);
+        __syncwarp();
+        p2(cur, sel);
+        fin_out(std::true_type{}, k, cur, sel);
+        __syncwarp();
+    }
+    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)sargs[s].actstep;
+    if (p.act_hist != nullptr) {
+        for (int s = lane; s < S; s += 32) {
+            unsigned csum = 0;
+            for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
+            atomicAdd(&hist[sargs[s].sarg], csum - (unsigned)flushpt[s]);
+        }
+        __syncwarp();
+        for (int a = lane; a < A; a += 32)
+            if (hist[a]) atomicAdd(p.act_hist + a, (unsigned long long)hist[a]);
+    }
+    if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, (unsigned long long)bad);
+}
+
 // ---- general-shape walker: tables in global memory, one row at a time ----------------------
 __host__ __device__ inline size_t walk_inst_bytes(int S, int A) {
     const size_t ncell = (size_t)S * A;
@@ -585,12 +944,14 @@ static int pick_warps_per_cta(long long n_inst, size_t wb, int sms) {
     return best;
 }
 
-template <typename RT, typename OT, bool OV>
+template <typename RT, typename OT, bool OV, int SP>   // SP: 0 = k_stream_rows, 1 + flags = k_stream_rows_sp<flags>
 static int launch_rows(const StreamArgs &a, cudaStream_t st) {
     const size_t wb = rows_warp_bytes(a.S, a.A);
     const int wpc = pick_warps_per_cta(a.n_inst, wb, sm_count());
     const size_t smem = kRowsCtaFixedBytes + wb * wpc;
-    auto kern = k_stream_rows<RT, OT, OV>;
+    void (*kern)(const StreamArgs, const int, const unsigned);
+    if constexpr (SP == 0) kern = k_stream_rows<RT, OT, OV>;
+    else kern = k_stream_rows_sp<RT, OT, OV, SP - 1>;
     static size_t configured = 0;   // per template instance; growing only
     if (smem > configured) {
         DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
@@ -610,7 +971,7 @@ static int launch_rows(const StreamArgs &a, cudaStream_t st) {
         c.out_activation = a.out_activation + lo * a.S;
         const long long grid = (c.n_inst + wpc - 1) / wpc;
         kern<<<(unsigned)grid, wpc * 32, smem, st>>>(c, wpc, (unsigned)wb);
-        DCARL_LAUNCH_CHECK("k_stream_rows");
+        DCARL_LAUNCH_CHECK(SP ? "k_stream_rows_sp" : "k_stream_rows");
     }
     return 0;
 }
@@ -624,11 +985,29 @@ static int launch_walk(const StreamArgs &a, void *ws, cudaStream_t st) {
     return 0;
 }
 
+template <typename RT, typename OT, bool OV>
+static int dispatch_sp(const StreamArgs &a, int sp, cudaStream_t st) {
+    switch (sp) {
+        case 0: return launch_rows<RT, OT, OV, 0>(a, st);
+        case 1: return launch_rows<RT, OT, OV, 1>(a, st);
+        default: break;
+    }
+    // experimental flag combinations: float32 rows, float32 outputs only
+    if constexpr (std::is_same<RT, float>::value && std::is_same<OT, float>::value) {
+        switch (sp) {
+            case 2: return launch_rows<RT, OT, OV, 2>(a, st);
+            case 3: return launch_rows<RT, OT, OV, 3>(a, st);
+            case 4: return launch_rows<RT, OT, OV, 4>(a, st);
+            default: break;
+        }
+    }
+    return bad_arg(19, "this kernel variant is built for float32 rows and outputs only");
+}
+
 template <typename RT, typename OT>
-static int dispatch_ov(const StreamArgs &a, bool rows, void *ws, cudaStream_t st) {
-    if (a.out_overall)
-        return rows ? launch_rows<RT, OT, true>(a, st) : launch_walk<RT, OT, true>(a, ws, st);
-    return rows ? launch_rows<RT, OT, false>(a, st) : launch_walk<RT, OT, false>(a, ws, st);
+static int dispatch_ov(const StreamArgs &a, bool rows, int sp, void *ws, cudaStream_t st) {
+    if (a.out_overall) return rows ? dispatch_sp<RT, OT, true>(a, sp, st) : launch_walk<RT, OT, true>(a, ws, st);
+    return rows ? dispatch_sp<RT, OT, false>(a, sp, st) : launch_walk<RT, OT, false>(a, ws, st);
 }
 
 }  // namespace dcarl
@@ -661,13 +1040,15 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     if (!out_activation_step) return bad_arg(13, "out_activation_step is null");
     if (n_steps > 0 && (!idx || !act || !R)) return bad_arg(1, "idx/act/R is null");
     if (n_steps > 0 && (!out_value || !out_act)) return bad_arg(10, "out_value/out_act is null");
-    if (variant < 0 || variant > 2) return bad_arg(19, "variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 6) return bad_arg(19, "variant must be in 0..6");
     if ((n_inst + 3) / 4 > 0x7fffffffll) return bad_arg(5, "n_inst too large for one launch");
 
     const bool fits = kRowsCtaFixedBytes + rows_warp_bytes(S, A) <= kMaxSmemPerCta;
     bool rows = fits;
     if (variant == 1) rows = false;
-    if (variant == 2 && !fits) return bad_arg(19, "the S*A table does not fit shared memory");
+    if (variant >= 2 && !fits) return bad_arg(19, "the S*A table does not fit shared memory");
+    const int sp = variant >= 3 ? variant - 2 : 0;   // 3: pipelined kernel, 4..6: + experiment flags
+    if (sp >= 2 && ((sp - 1) & 1) && (S > 32 || A > 16)) return bad_arg(19, "ballot-peer experiment needs S <= 32, A <= 16");
     if (!rows) {
         const size_t need = dcarl_stream_bounds_ws(n_inst, n_steps, S, A);
         if (!ws || ws_bytes < need) return bad_arg(17, "workspace too small (see dcarl_stream_bounds_ws)");
@@ -685,8 +1066,9 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     a.bonus = p->activation_bonus; a.n_thres = p->n_thres; a.rule_act = p->rule_act;
     cudaStream_t st = (cudaStream_t)stream;
     if (r_is_f64)
-        return out_is_f64 ? dispatch_ov<double, double>(a, rows, ws, st) : dispatch_ov<double, float>(a, rows, ws, st);
-    return out_is_f64 ? dispatch_ov<float, double>(a, rows, ws, st) : dispatch_ov<float, float>(a, rows, ws, st);
+        return out_is_f64 ? dispatch_ov<double, double>(a, rows, sp, ws, st)
+                          : dispatch_ov<double, float>(a, rows, sp, ws, st);
+    return out_is_f64 ? dispatch_ov<float, double>(a, rows, sp, ws, st) : dispatch_ov<float, float>(a, rows, sp, ws, st);
 }
 
 extern "C" int dcarl_cell_values(const int32_t *n, const double *sum, const double *sumsq, const int32_t *act,
