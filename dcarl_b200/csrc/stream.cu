@@ -10,16 +10,16 @@
 //   k_stream_rows  — the product path.  One warp owns one instance; the S x A moment
 //                    table, the value table and the per-state (max, argmax, bound on the
 //                    runner-up) live in shared memory.  32 consecutive rows are processed
-//                    at once, one row per lane:
-//                      phase 1  cell moments: peers of the same cell inside the batch are
-//                               found with match.any and prefix-summed in time order,
-//                               then every lane evaluates its bound in float64;
-//                      phase 2  argmax: a row cannot move its state's argmax unless it
-//                               updates the argmax cell to below the runner-up bound or
-//                               lifts another cell above that bound; rows that cannot are
-//                               resolved in parallel (the running max is the value of the
-//                               latest argmax-cell row), the rare row that might is
-//                               replayed exactly with a warp-wide top-2 scan.
+//                    at once, one row per lane, in two stages skewed by one batch:
+//                      moments   peers of the same cell inside the batch are found with
+//                                match.any and prefix-summed in time order, then every lane
+//                                evaluates its bound in float64;
+//                      selector  a row cannot move its state's argmax unless it updates the
+//                                argmax cell to below the runner-up bound or lifts another
+//                                cell above that bound; rows that cannot are resolved in
+//                                parallel (the running max is the value of the latest
+//                                argmax-cell row), the rare row that might is replayed
+//                                exactly with a warp-wide top-2 scan.
 //   k_stream_walk  — any shape: tables in a global-memory workspace, rows replayed one
 //                    at a time with lanes over actions.  Fallback + cross-check.
 #include <math_constants.h>
@@ -164,289 +164,36 @@ __host__ __device__ inline size_t rows_warp_bytes(int S, int A) {
     return (b + 15) & ~(size_t)15;
 }
 constexpr size_t kRowsCtaFixedBytes = 0;
-constexpr int kRowsMaxWarps = 7;
+constexpr int kRowsMaxWarps = 28;   // 72 registers per thread: 28 resident warps per SM, 7 per scheduler
+
+// ---- row kernel: one warp per instance, 32 rows per batch, software-pipelined ----------------
+// The loop is skewed by one batch.  The moment stage of batch b+1 (row loads, peer matching,
+// running moments, bound) touches only {cnt, s1, s2}; the selector stage of batch b (argmax
+// bookkeeping, overall_value scan, output stores) touches only {val, state records}.  Placing
+// the two in the same straight-line region gives every warp two independent dependency chains:
+// with 7 warps per scheduler (config 2 is one resident wave) the kernel is bound by the length
+// of a warp's own chain, not by issue slots.  The first selector round is peeled out of its retry
+// loop so that it shares a basic block with the next batch's moment loads; the match.any pair is
+// issued before that round and consumed after it.  The warp index is broadcast from lane 0 so
+// that the compiler knows every loop bound is warp-uniform (no divergence fallbacks around the
+// warp-synchronous intrinsics).  float32 outputs scan the in-batch overall_value deltas in
+// float32 (the running total stays float64; activation jumps, rare, are added in float64).
+// Lanes of the same state (ms) and of the same action (ma); their AND is the cell mask.
+// match.any takes about one round per distinct value in the warp, so two matches (~13 + ~11
+// distinct values) beat one match on the cell key (~28); one ballot per key bit was measured
+// slower still (more instructions: the kernel is within 20 % of issue-bound).
+__device__ __forceinline__ void peer_masks(int s, int a, unsigned &ms, unsigned &ma) {
+    ms = __match_any_sync(FULL_MASK, s);
+    ma = __match_any_sync(FULL_MASK, a);
+}
+
+#ifdef DCARL_DEBUG_TIMING
+__device__ unsigned long long g_rows_timing[4 * 65536];   // per instance: start ns, end ns, smid, hw warp id
+#endif
 
 template <typename RT, typename OT, bool OVERALL>
-__global__ void __launch_bounds__(kRowsMaxWarps * 32, 4)
+__global__ void __launch_bounds__(kRowsMaxWarps * 32, 1)
 k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_bytes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = lane_id();
-    // broadcast from lane 0: tells the compiler the warp index (hence `inst` and every loop bound)
-    // is warp-uniform, so the warp-synchronous intrinsics below need no divergence fallbacks
-    const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
-
-    const long long inst = (long long)blockIdx.x * warps_per_cta + warp;
-    if (inst >= p.n_inst) return;
-
-    const int S = p.S, A = p.A, ncell = S * A;
-    StateHot *hot = reinterpret_cast<StateHot *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
-    StateArg *sargs = reinterpret_cast<StateArg *>(hot + S);
-    Cell *cells = reinterpret_cast<Cell *>(sargs + S);
-    unsigned *cnt = reinterpret_cast<unsigned *>(cells + ncell);
-    int *flushpt = reinterpret_cast<int *>(cnt + ncell);
-    unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
-
-    for (int c = lane; c < ncell; c += 32) {
-        cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
-        cells[c].val = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
-    }
-    for (int a = lane; a < A; a += 32) hist[a] = 0u;
-    __syncwarp();
-    {
-        double m0, sec0; int g0;
-        warp_top2(&cells[0].val, 3, A, m0, g0, sec0);   // every state starts identical
-        StateHot h0;
-        h0.smax = m0; h0.sub2 = runner_up_bound(sec0, m0);
-        StateArg a0;
-        a0.sarg = g0; a0.actstep = -1;                                          // ST1:58
-        for (int s = lane; s < S; s += 32) { hot[s] = h0; sargs[s] = a0; flushpt[s] = 0; }
-    }
-    __syncwarp();
-
-    const unsigned bit = 1u << lane;
-    const unsigned lt = bit - 1u, le = lt | bit, gt = ~le;
-    const unsigned n_steps = p.n_steps;
-    const double c_h = p.c_h, cap = p.cap, bonus = p.bonus;
-    const int rule = p.rule_act;
-    const unsigned n_thres = (unsigned)p.n_thres;
-
-    // One 32-bit element index addresses all six arrays (the host keeps n_inst*n_steps of a launch
-    // below 2^32): an address is a single IMAD.WIDE off a constant-bank base, no live pointers.
-    const int *__restrict__ gidx = p.idx;
-    const int *__restrict__ gact = p.act;
-    const RT *__restrict__ gR = reinterpret_cast<const RT *>(p.R);
-    OT *__restrict__ oval = reinterpret_cast<OT *>(p.out_value);
-    int *__restrict__ oact = p.out_act;
-    OT *__restrict__ oall = reinterpret_cast<OT *>(p.out_overall);
-    const unsigned ebase = (unsigned)inst * n_steps + lane;
-
-    double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
-    unsigned bad = 0;     // lane-local count of out-of-range rows
-
-    // software prefetch: rows of batch b+1 are requested while batch b is processed
-    int n_idx = 0, n_act = 0;
-    RT n_R = RT(0);
-    if ((unsigned)lane < n_steps) { n_idx = ld_stream(gidx + ebase); n_act = ld_stream(gact + ebase); n_R = ld_stream(gR + ebase); }
-
-    // One batch of 32 rows.  TAIL = the ragged last batch (lanes past the end of the stream are
-    // inactive); full batches compile without any of the activity predicates.
-    auto batch = [&](auto tail_tag, const unsigned k) {
-        constexpr bool TAIL = decltype(tail_tag)::value;
-        const bool in_stream = TAIL ? (k < n_steps) : true;
-        // out-of-range idx / act are clamped (memory safety) and counted: bad_rows != 0 is an error
-        // for the caller, the outputs of such an instance are unspecified
-        const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
-        const int a = (int)min((unsigned)n_act, (unsigned)(A - 1));
-        if (in_stream && (s_in != n_idx || a != n_act)) bad++;
-        const RT rin = n_R;
-        const double r = (double)rin;
-        const unsigned e = ebase + (k - lane);
-        if (k + 32 < n_steps) { n_idx = ld_stream(gidx + e + 32); n_act = ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
-        const bool active = in_stream;
-        // inactive lanes get a private key so they match nobody; their table index is clamped to 0
-        const int s = active ? s_in : (0x40000000 | lane);
-        const int sx = active ? s_in : 0;
-        const int kx = active ? s_in * A + a : 0;
-
-        // ---- phase 1: running moments of every row's cell, in time order -------------------
-        // peers of the same state / the same cell.  match.any takes about one round per distinct
-        // value in the warp, so the cell mask is the AND of a state match and an action match
-        // (~13 + ~11 distinct values) rather than a match on the cell key (~28).
-        const unsigned ms = __match_any_sync(FULL_MASK, s);
-        const unsigned mk = ms & __match_any_sync(FULL_MASK, a);
-        Cell *cell = cells + kx;
-        double acc1 = cell->s1, acc2 = cell->s2;
-        const unsigned n0 = cnt[kx];
-        // the state records are not touched by phase 1: fetch them now, under its latency
-        StateHot *sh = hot + sx;
-        StateArg *sa = sargs + sx;
-        StateHot h = *sh;
-        StateArg ga = *sa;
-        unsigned earlier = mk & lt;
-        {
-            // the two oldest peers straight-line (independent shuffles), a loop only beyond that
-            const unsigned e1 = earlier & (earlier - 1);
-            const RT r1 = __shfl_sync(FULL_MASK, rin, earlier ? (__ffs(earlier) - 1) : lane);
-            const RT r2 = __shfl_sync(FULL_MASK, rin, e1 ? (__ffs(e1) - 1) : lane);
-            if (earlier) { const double x = (double)r1; acc1 += x; acc2 = fma(x, x, acc2); }
-            if (e1) { const double x = (double)r2; acc1 += x; acc2 = fma(x, x, acc2); }
-            earlier = e1 & (e1 - 1);
-        }
-        while (__any_sync(FULL_MASK, earlier != 0)) {
-            const RT rj = __shfl_sync(FULL_MASK, rin, earlier ? (__ffs(earlier) - 1) : lane);
-            if (earlier) { const double x = (double)rj; acc1 += x; acc2 = fma(x, x, acc2); earlier &= earlier - 1; }
-        }
-        acc1 += r;
-        acc2 = fma(r, r, acc2);
-        const unsigned n = n0 + __popc(mk & lt) + 1u;
-        __syncwarp();
-        if (active && (mk & gt) == 0) { cnt[kx] = n; cell->s1 = acc1; cell->s2 = acc2; }
-        const bool upd = active && n > n_thres;                                   // ST1:86
-        const double v = cell_value(n, acc1, acc2, a == rule, c_h, cap);
-
-        // ---- phase 2: per-row (max, argmax) of the row's state ----------------------------
-        // Round 1 assumes nobody's argmax moves; a row that might move it is replayed exactly and
-        // the rows after it retry (rare).
-        const int ast = ga.actstep;
-        double m_out = 0.0, mprev_out = 0.0;   // the state's max just after / just before this row
-        int g_out = -1;
-        unsigned pend = __ballot_sync(FULL_MASK, active);
-        bool mine = active;
-        for (;;) {
-            const double c_ms0 = h.smax, c_ub = h.sub2;
-            const int c_g = ga.sarg;
-            const bool T = mine && upd && a == c_g;        // row refreshes the argmax cell of its state
-            const unsigned tm = __ballot_sync(FULL_MASK, T);
-            const unsigned cand = tm & ms & lt;            // earlier argmax-cell rows of my state
-            const int jp = cand ? (31 - __clz(cand)) : lane;
-            const double vp = shfl_f64(v, jp);
-            const double m_prev = cand ? vp : c_ms0;       // the state's max just before this row ...
-            const double m_k = T ? v : m_prev;             // ... and just after it (if nobody's argmax moves)
-            // a row keeps the argmax if it refreshes the argmax cell to above the runner-up bound, or
-            // another cell to at most that bound (and below the running max)
-            bool fail = mine && upd && (T ? !(v > c_ub) : !(v <= c_ub && v < m_k));
-            // a non-argmax row that rises above the bound but stays below the max keeps the argmax; it
-            // is now the exact runner-up (v > bound >= every other cell).  If no later row of its
-            // state follows in this batch it re-centres the bound itself instead of forcing a replay.
-            const bool lift = fail && !T && v < m_k && (ms & gt) == 0;
-            if (lift) fail = false;
-            const unsigned fm = __ballot_sync(FULL_MASK, fail);
-            const unsigned fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;   // pending rows before the first doubtful one
-            __syncwarp();   // every lane has consumed its state record before a peer overwrites it
-            if (mine && (fin & bit)) {
-                g_out = c_g; m_out = m_k; mprev_out = m_prev;
-                if (upd && (mk & fin & gt) == 0) cell->val = v;
-                if ((ms & fin & gt) == 0) sh->smax = m_k;
-                if (lift) sh->sub2 = runner_up_bound(v, m_k);
-            }
-            if (fm == 0) break;
-            // ---- exact replay of the first doubtful row j ------------------------------------
-            const int j = __ffs(fm) - 1;
-            __syncwarp();
-            const int sj = __shfl_sync(FULL_MASK, s, j);
-            const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
-            if (lane == j) cell->val = v;
-            __syncwarp();
-            const int old_g = sargs[sj].sarg;
-            double mx, second; int arg;
-            warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
-            if (arg != old_g) {
-                // rows (flushpt, t_j) of this state were emitted with old_g: account for them
-                unsigned csum = 0;
-                for (int q = lane; q < A; q += 32) csum += cnt[sj * A + q];
-                const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
-                if (lane == j) { hist[old_g] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1; }
-            }
-            if (lane == j) {
-                g_out = arg; m_out = mx; mprev_out = m_prev;
-                sh->smax = mx; sh->sub2 = runner_up_bound(second, mx); sa->sarg = arg;
-            }
-            __syncwarp();
-            pend &= ~(fin | (1u << j));
-            mine = mine && lane > j;
-            if (pend == 0) break;
-            h = *sh;
-            ga = *sa;
-        }
-
-        // ---- activation step (ST1:98-99): first row of a state whose argmax is not the rule action
-        unsigned need = 0;
-        const bool any_need = __any_sync(FULL_MASK, active && ast == -1 && g_out != rule);   // warp-uniform
-        if (any_need) {   // rare: once per state
-            need = __ballot_sync(FULL_MASK, active && ast == -1 && g_out != rule) & ms;
-            __syncwarp();
-            if (need && lane == __ffs(need) - 1) {
-                unsigned csum = 0;
-                for (int q = 0; q < A; ++q) csum += cnt[sx * A + q];
-                sa->actstep = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
-            }
-        }
-        if (OVERALL) {                                                            // ST2:99-105
-            // contribution of the row's state after the row, minus before it; prefix-summed over the batch
-            const bool act_before = ast != -1;
-            double d;
-            if (!any_need) {
-                // no state activates in this batch (warp-uniform branch): the bonus cancels in the difference
-                d = (active && act_before) ? m_out - mprev_out : 0.0;
-            } else {
-                const bool act_now = act_before || (need & le) != 0, act_prev = act_before || (need & lt) != 0;
-                d = active ? (act_now ? m_out + bonus : 0.0) - (act_prev ? mprev_out + bonus : 0.0) : 0.0;
-            }
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double o = __shfl_up_sync(FULL_MASK, d, off);
-                if (lane >= off) d += o;
-            }
-            const double ov = total + d;
-            total += shfl_f64(d, 31);
-            if (in_stream) st_stream(oall + e, (OT)ov);
-        }
-        if (in_stream) {
-            st_stream(oval + e, (OT)m_out);
-            st_stream(oact + e, g_out);
-        }
-        __syncwarp();   // table writes of this batch are ordered before the next batch's reads
-    };
-    unsigned k = lane;
-    for (; k - lane + 32 <= n_steps; k += 32) batch(std::false_type{}, k);
-    if (k - lane < n_steps) batch(std::true_type{}, k);
-    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)sargs[s].actstep;
-    if (p.act_hist != nullptr) {
-        // rows since the last argmax change of each state carry the state's current argmax
-        for (int s = lane; s < S; s += 32) {
-            unsigned csum = 0;
-            for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
-            atomicAdd(&hist[sargs[s].sarg], csum - (unsigned)flushpt[s]);
-        }
-        __syncwarp();
-        for (int a = lane; a < A; a += 32)
-            if (hist[a]) atomicAdd(p.act_hist + a, (unsigned long long)hist[a]);
-    }
-    if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, (unsigned long long)bad);
-}
-
-// ---- software-pipelined row kernel ---------------------------------------------------------
-// Same tables, same per-row logic and the same results as k_stream_rows; the loop is skewed by
-// one batch.  The moment stage of batch b+1 (row loads, peer matching, running moments, bound)
-// touches only {cnt, s1, s2}; the selector stage of batch b (argmax bookkeeping, overall_value
-// scan, output stores) touches only {val, state records}.  Placing the two in the same
-// straight-line region gives every warp two independent dependency chains, which is what the
-// 7-warps-per-scheduler residency of config 2 lacks.  The first selector round is peeled out
-// of its retry loop so that it shares a basic block with the next batch's moment loads.
-// float32 outputs scan the in-batch overall_value deltas in float32 (the running total stays
-// float64; activation jumps, rare, are added in float64).
-// Lanes of the same state (ms) and of the same cell (mk).  match.any takes about one round per
-// distinct value in the warp, so the cell mask is the AND of a state match and an action match
-// rather than a match on the cell key.  BALLOT: the same masks from one ballot per key bit
-// (nb_s + nb_a ballots; short dependency chain, more instructions).
-template <bool BALLOT>
-__device__ __forceinline__ void peer_masks(int s, int a, bool active, unsigned &ms, unsigned &mk) {
-    if (!BALLOT) {
-        ms = __match_any_sync(FULL_MASK, s);
-        mk = ms & __match_any_sync(FULL_MASK, a);
-    } else {
-        // experiment build: 5 state bits, 4 action bits (S <= 32, A <= 16; checked by the host)
-        unsigned m = __ballot_sync(FULL_MASK, active);
-#pragma unroll
-        for (int b = 0; b < 5; ++b) {
-            const bool on = (s >> b) & 1;
-            const unsigned bal = __ballot_sync(FULL_MASK, on);
-            m &= on ? bal : ~bal;
-        }
-        ms = active ? m : (1u << lane_id());
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const bool on = (a >> b) & 1;
-            const unsigned bal = __ballot_sync(FULL_MASK, on);
-            m &= on ? bal : ~bal;
-        }
-        mk = active ? m : (1u << lane_id());
-    }
-}
-
-template <typename RT, typename OT, bool OVERALL, int FLAGS>
-__global__ void __launch_bounds__(kRowsMaxWarps * 32, 4)
-k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
     // broadcast from lane 0: tells the compiler the warp index (hence `inst` and every loop bound)
@@ -481,14 +228,22 @@ k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned war
     }
     __syncwarp();
 
+#ifdef DCARL_DEBUG_TIMING
+    if (lane == 0 && inst < 65536) {
+        unsigned long long t; unsigned smid, wid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        g_rows_timing[inst * 4 + 0] = t; g_rows_timing[inst * 4 + 2] = smid; g_rows_timing[inst * 4 + 3] = wid;
+    }
+#endif
     const unsigned bit = 1u << lane;
     const unsigned lt = bit - 1u, le = lt | bit, gt = ~le;
     const unsigned n_steps = p.n_steps;
     const double c_h = p.c_h, cap = p.cap, bonus = p.bonus;
     const int rule = p.rule_act;
     const unsigned n_thres = (unsigned)p.n_thres;
-    constexpr bool BALLOT_PEERS = (FLAGS & 1) != 0;
-    constexpr bool SCAN_F32 = std::is_same<OT, float>::value && (FLAGS & 2) == 0;
+    constexpr bool SCAN_F32 = std::is_same<OT, float>::value;
 
     const int *__restrict__ gidx = p.idx;
     const int *__restrict__ gact = p.act;
@@ -523,10 +278,11 @@ k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned war
         bool any_need;
     };
 
-    // ---- moment stage, part a: consume the prefetched rows, request the batch after, find the
-    // peers, load the cell moments, fetch the returns of the two oldest in-batch peers.  Only
-    // issues work: nothing here waits on a shuffle or a shared-memory load.
-    auto p1a = [&](auto tail_tag, const unsigned k, Rows &r, Mom &m) {
+    // ---- moment stage, issue part: consume the prefetched rows, request the batch after, start
+    // the two peer matches and the cell loads.  Nothing here waits on a result: match.any takes
+    // ~100 cycles per call, so its consumers sit in p1a_peers, after the selector stage of the
+    // previous batch.
+    auto p1a_issue = [&](auto tail_tag, const unsigned k, Rows &r, Mom &m) {
         constexpr bool TAIL = decltype(tail_tag)::value;
         const bool in_stream = TAIL ? (k < n_steps) : true;
         const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
@@ -540,11 +296,16 @@ k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned war
         r.sx = in_stream ? s_in : 0;
         r.a = a;
         r.kx = in_stream ? s_in * A + a : 0;
-        peer_masks<BALLOT_PEERS>(r.s, a, in_stream, r.ms, r.mk);
+        peer_masks(r.s, a, r.ms, r.mk);   // mk = action peers until p1a_peers
         const Cell *cell = cells + r.kx;
         m.acc1 = cell->s1; m.acc2 = cell->s2;
+        r.n = cnt[r.kx];
+    };
+    // peers part: the cell mask, the row's sample count, the returns of the two oldest in-batch peers
+    auto p1a_peers = [&](Rows &r, Mom &m) {
+        r.mk &= r.ms;
         m.earlier = r.mk & lt;
-        r.n = cnt[r.kx] + __popc(m.earlier) + 1u;
+        r.n += __popc(m.earlier) + 1u;
         const unsigned e1 = m.earlier & (m.earlier - 1);
         m.r1 = __shfl_sync(FULL_MASK, m.rin, m.earlier ? (__ffs(m.earlier) - 1) : lane);
         m.r2 = __shfl_sync(FULL_MASK, m.rin, e1 ? (__ffs(e1) - 1) : lane);
@@ -618,7 +379,9 @@ k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned war
             o.mprev_out = done ? m_prev : o.mprev_out;
             if (done & upd & ((mk & fin & gt) == 0)) cell->val = v;
             if (done & ((ms & fin & gt) == 0)) sh->smax = m_k;
-            if (done & lift) sh->sub2 = runner_up_bound(v, m_k);
+            if (__any_sync(FULL_MASK, lift)) {   // rare
+                if (done & lift) sh->sub2 = runner_up_bound(v, m_k);
+            }
         };
         round();
         if (fm != 0) {
@@ -719,14 +482,16 @@ k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned war
     Mom mom;
     Sel sel;
     if (nfull) {
-        p1a(std::false_type{}, k, cur, mom);
+        p1a_issue(std::false_type{}, k, cur, mom);
+        p1a_peers(cur, mom);
         p1_peers(mom);
         p1b(cur, mom);
         __syncwarp();
         for (unsigned b = 1; b < nfull; ++b) {
             Rows nxt;
-            p1a(std::false_type{}, k + 32, nxt, mom);   // reads {cnt, s1, s2} only
+            p1a_issue(std::false_type{}, k + 32, nxt, mom);   // reads {cnt, s1, s2} only
             p2(cur, sel);                               // reads/writes {val, state records}; cnt read-only
+            p1a_peers(nxt, mom);
             p1_peers(mom);
             p1b(nxt, mom);                              // writes {cnt, s1, s2}
             fin_out(std::false_type{}, k, cur, sel);
@@ -740,7 +505,8 @@ k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned war
         k += 32;
     }
     if (k - lane < n_steps) {   // ragged last batch: lanes past the end of the stream are inactive
-        p1a(std::true_type{}, k, cur, mom);
+        p1a_issue(std::true_type{}, k, cur, mom);
+        p1a_peers(cur, mom);
         p1_peers(mom);
         p1b(cur, mom);
         __syncwarp();
@@ -748,6 +514,13 @@ k_stream_rows_sp(const StreamArgs p, const int warps_per_cta, const unsigned war
         fin_out(std::true_type{}, k, cur, sel);
         __syncwarp();
     }
+#ifdef DCARL_DEBUG_TIMING
+    if (lane == 0 && inst < 65536) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_rows_timing[inst * 4 + 1] = t;
+    }
+#endif
     for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)sargs[s].actstep;
     if (p.act_hist != nullptr) {
         for (int s = lane; s < S; s += 32) {
@@ -924,34 +697,28 @@ __global__ void __launch_bounds__(256) k_cell_values(const int *__restrict__ n, 
 
 // ---- host side -------------------------------------------------------------------------------
 static const size_t kMaxSmemPerCta = 227 * 1024;
-static const size_t kSmemPerSm = 228 * 1024;
 
-// warps (= instances) per CTA: minimise the work of the busiest SM, then prefer larger CTAs
+// Warps (= instances) per CTA.  Measured on config 2 (4096 x 20000, one resident wave): one 28-warp
+// CTA per SM 0.96 ms, four 7-warp CTAs 1.07 ms — the arbiter favours the warps of some CTAs, they
+// finish early and leave their scheduler under-occupied.  With many waves (config 5, 32768 x 500)
+// small CTAs refill an SM sooner: 4 warps 0.180 ms, 28 warps 0.188 ms.
 static int pick_warps_per_cta(long long n_inst, size_t wb, int sms) {
-    int best = 1;
-    long long best_cost = -1;
-    for (int w = 1; w <= kRowsMaxWarps; ++w) {
-        const size_t cta = kRowsCtaFixedBytes + wb * w;
-        if (cta > kMaxSmemPerCta) break;
-        long long resident = (long long)(kSmemPerSm / (cta + 1024)) * w;   // warps per SM that fit
-        if (resident > 28) resident = 28;                                   // 72 registers per thread
-        const long long ctas = (n_inst + w - 1) / w;
-        const long long per_sm = (ctas + sms - 1) / sms * w;                // warps the busiest SM runs
-        const long long rounds = (per_sm + resident - 1) / resident;
-        const long long cost = rounds * resident * 1000 + per_sm;          // full rounds dominate
-        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = w; }
+    long long fit = (long long)(kMaxSmemPerCta / wb);          // warps whose tables fit one CTA
+    if (fit > kRowsMaxWarps) fit = kRowsMaxWarps;
+    if (fit < 1) fit = 1;
+    if (n_inst <= fit * sms) {                                 // one wave: one CTA per SM
+        const long long w = (n_inst + sms - 1) / sms;
+        return (int)(w < 1 ? 1 : w);
     }
-    return best;
+    return (int)(fit < 4 ? fit : 4);
 }
 
-template <typename RT, typename OT, bool OV, int SP>   // SP: 0 = k_stream_rows, 1 + flags = k_stream_rows_sp<flags>
+template <typename RT, typename OT, bool OV>
 static int launch_rows(const StreamArgs &a, cudaStream_t st) {
     const size_t wb = rows_warp_bytes(a.S, a.A);
     const int wpc = pick_warps_per_cta(a.n_inst, wb, sm_count());
     const size_t smem = kRowsCtaFixedBytes + wb * wpc;
-    void (*kern)(const StreamArgs, const int, const unsigned);
-    if constexpr (SP == 0) kern = k_stream_rows<RT, OT, OV>;
-    else kern = k_stream_rows_sp<RT, OT, OV, SP - 1>;
+    auto kern = k_stream_rows<RT, OT, OV>;
     static size_t configured = 0;   // per template instance; growing only
     if (smem > configured) {
         DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
@@ -971,7 +738,7 @@ static int launch_rows(const StreamArgs &a, cudaStream_t st) {
         c.out_activation = a.out_activation + lo * a.S;
         const long long grid = (c.n_inst + wpc - 1) / wpc;
         kern<<<(unsigned)grid, wpc * 32, smem, st>>>(c, wpc, (unsigned)wb);
-        DCARL_LAUNCH_CHECK(SP ? "k_stream_rows_sp" : "k_stream_rows");
+        DCARL_LAUNCH_CHECK("k_stream_rows");
     }
     return 0;
 }
@@ -985,29 +752,11 @@ static int launch_walk(const StreamArgs &a, void *ws, cudaStream_t st) {
     return 0;
 }
 
-template <typename RT, typename OT, bool OV>
-static int dispatch_sp(const StreamArgs &a, int sp, cudaStream_t st) {
-    switch (sp) {
-        case 0: return launch_rows<RT, OT, OV, 0>(a, st);
-        case 1: return launch_rows<RT, OT, OV, 1>(a, st);
-        default: break;
-    }
-    // experimental flag combinations: float32 rows, float32 outputs only
-    if constexpr (std::is_same<RT, float>::value && std::is_same<OT, float>::value) {
-        switch (sp) {
-            case 2: return launch_rows<RT, OT, OV, 2>(a, st);
-            case 3: return launch_rows<RT, OT, OV, 3>(a, st);
-            case 4: return launch_rows<RT, OT, OV, 4>(a, st);
-            default: break;
-        }
-    }
-    return bad_arg(19, "this kernel variant is built for float32 rows and outputs only");
-}
-
 template <typename RT, typename OT>
-static int dispatch_ov(const StreamArgs &a, bool rows, int sp, void *ws, cudaStream_t st) {
-    if (a.out_overall) return rows ? dispatch_sp<RT, OT, true>(a, sp, st) : launch_walk<RT, OT, true>(a, ws, st);
-    return rows ? dispatch_sp<RT, OT, false>(a, sp, st) : launch_walk<RT, OT, false>(a, ws, st);
+static int dispatch_ov(const StreamArgs &a, bool rows, void *ws, cudaStream_t st) {
+    if (a.out_overall)
+        return rows ? launch_rows<RT, OT, true>(a, st) : launch_walk<RT, OT, true>(a, ws, st);
+    return rows ? launch_rows<RT, OT, false>(a, st) : launch_walk<RT, OT, false>(a, ws, st);
 }
 
 }  // namespace dcarl
@@ -1040,15 +789,13 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     if (!out_activation_step) return bad_arg(13, "out_activation_step is null");
     if (n_steps > 0 && (!idx || !act || !R)) return bad_arg(1, "idx/act/R is null");
     if (n_steps > 0 && (!out_value || !out_act)) return bad_arg(10, "out_value/out_act is null");
-    if (variant < 0 || variant > 6) return bad_arg(19, "variant must be in 0..6");
+    if (variant < 0 || variant > 2) return bad_arg(19, "variant must be 0, 1 or 2");
     if ((n_inst + 3) / 4 > 0x7fffffffll) return bad_arg(5, "n_inst too large for one launch");
 
     const bool fits = kRowsCtaFixedBytes + rows_warp_bytes(S, A) <= kMaxSmemPerCta;
     bool rows = fits;
     if (variant == 1) rows = false;
-    if (variant >= 2 && !fits) return bad_arg(19, "the S*A table does not fit shared memory");
-    const int sp = variant >= 3 ? variant - 2 : 0;   // 3: pipelined kernel, 4..6: + experiment flags
-    if (sp >= 2 && ((sp - 1) & 1) && (S > 32 || A > 16)) return bad_arg(19, "ballot-peer experiment needs S <= 32, A <= 16");
+    if (variant == 2 && !fits) return bad_arg(19, "the S*A table does not fit shared memory");
     if (!rows) {
         const size_t need = dcarl_stream_bounds_ws(n_inst, n_steps, S, A);
         if (!ws || ws_bytes < need) return bad_arg(17, "workspace too small (see dcarl_stream_bounds_ws)");
@@ -1066,10 +813,17 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     a.bonus = p->activation_bonus; a.n_thres = p->n_thres; a.rule_act = p->rule_act;
     cudaStream_t st = (cudaStream_t)stream;
     if (r_is_f64)
-        return out_is_f64 ? dispatch_ov<double, double>(a, rows, sp, ws, st)
-                          : dispatch_ov<double, float>(a, rows, sp, ws, st);
-    return out_is_f64 ? dispatch_ov<float, double>(a, rows, sp, ws, st) : dispatch_ov<float, float>(a, rows, sp, ws, st);
+        return out_is_f64 ? dispatch_ov<double, double>(a, rows, ws, st) : dispatch_ov<double, float>(a, rows, ws, st);
+    return out_is_f64 ? dispatch_ov<float, double>(a, rows, ws, st) : dispatch_ov<float, float>(a, rows, ws, st);
 }
+
+#ifdef DCARL_DEBUG_TIMING
+extern "C" int dcarl_debug_rows_timing(unsigned long long *host_out, int64_t n_inst) {
+    DCARL_CUDA(cudaDeviceSynchronize());
+    DCARL_CUDA(cudaMemcpyFromSymbol(host_out, g_rows_timing, sizeof(unsigned long long) * 4 * (size_t)n_inst));
+    return 0;
+}
+#endif
 
 extern "C" int dcarl_cell_values(const int32_t *n, const double *sum, const double *sumsq, const int32_t *act,
                                  int64_t count, const dcarl_params *p, double *out, dcarl_stream_t stream) {

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 80 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/launches_bench.log 2>&1
 echo "launch list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream_rows -s 2 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream_rows -s 3 -c 1 \
     -f -o gpurun_out/stream_rows python bench.py --steps 1 --warmup 3 --no-cpu --no-secondary > gpurun_out/ncu_full.log 2>&1
 echo "stream capture exit $?"
 if [ -n "$BOX" ]; then

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time the stream-kernel variants on the BASELINE config-2 workload and cross-check their outputs.
 
-    python tools/stream_sweep.py [--variants 2,3,4] [--steps 10] [--once] [--n-inst 4096]
+    python tools/stream_sweep.py [--variants 0,1] [--steps 10] [--once] [--n-inst 4096] [--n-steps 20000]
 
 One JSON line per variant (also appended to gpurun_out/stream_sweep.jsonl): kernel ms (CUDA events
 around `steps` back-to-back launches on the launching stream), scenario-steps/s, algorithmic GB/s
@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="2,3,4,5,6")
+    ap.add_argument("--variants", default="0")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n-inst", type=int, default=4096)
