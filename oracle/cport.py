@@ -25,8 +25,8 @@ def default_params(**kw):
 
 
 def build(force=False):
-    src = os.path.join(_DIR, "dcarl_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_DIR, f) for f in ("dcarl_oracle.c", "frenet_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _DIR, "-B", "libdcarl_oracle.so"],
                               stdout=subprocess.DEVNULL)
     return _SO
@@ -35,8 +35,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()
         _lib = C.CDLL(_SO)
         d = C.c_double
         _lib.orc_np_sum.restype = d
@@ -152,3 +151,76 @@ def rollout_cv(state0, action, steps, dt, radius, pass_x, speed_scale):
     if rc:
         raise ValueError("oracle: action out of range")
     return ret, st, tm
+
+
+# ---- Frenet candidate planner (oracle/frenet_oracle.c) ---------------------------------------
+FR_MAX_D, FR_MAX_T, FR_MAX_V = 16, 4, 8
+
+
+class FrenetParams(C.Structure):
+    """Field-for-field mirror of fr_params (frenet_oracle.c) / dcarl_frenet_params (the C ABI)."""
+    _fields_ = [("d_samples", C.c_double * FR_MAX_D), ("T_samples", C.c_double * FR_MAX_T),
+                ("tv_samples", C.c_double * FR_MAX_V), ("n_t", C.c_int32 * FR_MAX_T),
+                ("n_d", C.c_int32), ("n_T", C.c_int32), ("n_v", C.c_int32), ("n_pred", C.c_int32),
+                ("obstacles_considered", C.c_int32), ("pad_", C.c_int32),
+                ("dt", C.c_double), ("target_speed", C.c_double),
+                ("max_speed", C.c_double), ("max_accel", C.c_double), ("max_curvature", C.c_double),
+                ("robot_radius", C.c_double), ("move_gap", C.c_double),
+                ("kj", C.c_double), ("kt", C.c_double), ("kd", C.c_double), ("klat", C.c_double), ("klon", C.c_double)]
+
+
+def frenet_params(MAX_SPEED=50.0 / 3.6, MAX_ACCEL=10.0, MAX_CURVATURE=500.0, MAX_LEFT_WIDTH=-4, MAX_RIGHT_WIDTH=4,
+                  D_ROAD_W=2, DT=0.3, MAXT=4.2, MINT=4.0, TARGET_SPEED=30.0 / 3.6, D_T_S=15 / 3.6, N_S_SAMPLE=1,
+                  OBSTACLES_CONSIDERED=4, ROBOT_RADIUS=1, MOVE_GAP=1, KJ=0.1, KT=0.1, KD=1.0, KLAT=1.0, KLON=1.0):
+    """The module constants of JunctionTrajectoryPlanner.py:13-39 turned into the sample grids the
+    planner loops over (np.arange, like the reference)."""
+    p = FrenetParams()
+    d = np.arange(MAX_LEFT_WIDTH, MAX_RIGHT_WIDTH + 1, D_ROAD_W).astype(np.float64)
+    T = np.arange(MINT, MAXT, DT).astype(np.float64)
+    tv = np.arange(TARGET_SPEED - D_T_S * N_S_SAMPLE, TARGET_SPEED + D_T_S * N_S_SAMPLE, D_T_S).astype(np.float64)
+    assert len(d) <= FR_MAX_D and len(T) <= FR_MAX_T and len(tv) <= FR_MAX_V
+    p.d_samples[:len(d)] = d.tolist()
+    p.T_samples[:len(T)] = T.tolist()
+    p.tv_samples[:len(tv)] = tv.tolist()
+    p.n_t[:len(T)] = [len(np.arange(0.0, Ti, DT)) for Ti in T]
+    p.n_d, p.n_T, p.n_v = len(d), len(T), len(tv)
+    p.n_pred = len(np.arange(0.0, MAXT, DT))
+    p.obstacles_considered = int(OBSTACLES_CONSIDERED)
+    p.dt, p.target_speed = float(DT), float(TARGET_SPEED)
+    p.max_speed, p.max_accel, p.max_curvature = float(MAX_SPEED), float(MAX_ACCEL), float(MAX_CURVATURE)
+    p.robot_radius, p.move_gap = float(ROBOT_RADIUS), float(MOVE_GAP)
+    p.kj, p.kt, p.kd, p.klat, p.klon = float(KJ), float(KT), float(KD), float(KLAT), float(KLON)
+    return p
+
+
+def spline_build(xy):
+    """xy [n, 2] knots -> coef [n, 9] rows {s, ax, bx, cx, dx, ay, by, cy, dy} (cubic_spline_planner.py:18-45)."""
+    xy = _f64(xy)
+    coef = np.empty((xy.shape[0], 9))
+    rc = lib().orc_spline_build(_p(xy, C.c_double), C.c_int(xy.shape[0]), _p(coef, C.c_double))
+    if rc:
+        raise ValueError("oracle: knot count out of range")
+    return coef
+
+
+def frenet_plan(coef, knot_off, path_id, start, ego_xy, obs, n_obs, params, want_paths=True):
+    """n scenarios: see orc_frenet_plan.  Returns a dict of numpy arrays."""
+    coef, start, ego_xy = _f64(coef), _f64(start).reshape(-1, 5), _f64(ego_xy).reshape(-1, 2)
+    knot_off = np.ascontiguousarray(knot_off, np.int64)
+    path_id, n_obs = _i32(path_id), _i32(n_obs)
+    n = start.shape[0]
+    obs = _f64(obs).reshape(n, -1, 5) if np.size(obs) else np.zeros((n, 1, 5))
+    max_obs = obs.shape[1]
+    Cn = params.n_d * params.n_T * params.n_v
+    Tm = max(params.n_t[:params.n_T])
+    out = dict(index=np.empty(n, np.int32), cost=np.empty((n, Cn)), flags=np.empty((n, Cn), np.uint8),
+               n_valid=np.empty((n, Cn), np.int32), paths=np.empty((n, Cn, Tm, 2)) if want_paths else None,
+               traj=np.empty((n, Tm, 3)), traj_len=np.empty(n, np.int32))
+    lib().orc_frenet_plan(_p(coef, C.c_double), _p(knot_off, C.c_int64), _p(path_id, C.c_int32),
+                          _p(start, C.c_double), _p(ego_xy, C.c_double), _p(obs, C.c_double),
+                          _p(n_obs, C.c_int32), C.c_int(max_obs), C.c_int64(n), C.byref(params),
+                          _p(out["index"], C.c_int32), _p(out["cost"], C.c_double), _p(out["flags"], C.c_uint8),
+                          _p(out["n_valid"], C.c_int32),
+                          _p(out["paths"], C.c_double) if want_paths else None,
+                          _p(out["traj"], C.c_double), _p(out["traj_len"], C.c_int32))
+    return out

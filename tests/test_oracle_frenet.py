@@ -1,0 +1,67 @@
+"""The Frenet-planner oracle (oracle/frenet_oracle.c) against outputs of the reference planner
+itself (tests/golden/frenet.npz, made by tools/make_golden_frenet.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import cport
+from helpers_frenet import golden_batch, params_from_golden
+
+
+@pytest.fixture(scope="module")
+def g(golden):
+    return golden("frenet")
+
+
+def test_grids_match_the_reference_loops(g):
+    p = params_from_golden(g, cport.frenet_params)
+    assert (p.n_d, p.n_T, p.n_v) == (5, 1, 2)
+    assert list(p.n_t[:1]) == [g["x"].shape[2]] == [14]
+    assert p.n_pred == int(g["n_pred"].max()) == 15          # len(np.arange(0, 4.2, 0.3)): 14.000000000000002 -> 15
+    assert g["cost"].shape[1] == p.n_d * p.n_T * p.n_v
+
+
+def test_spline_coefficients(g):
+    for i in range(int(g["n_cases"])):
+        nk = int(g["n_knots"][i])
+        xy = np.stack([g["knots_x"][i, :nk], g["knots_y"][i, :nk]], axis=1)
+        coef = cport.spline_build(xy)
+        assert np.allclose(coef[:, 0], g["spline_s"][i, :nk], rtol=0, atol=1e-12)
+        for col, ref in ((1, g["spline_cx"][i]), (5, g["spline_cy"][i])):
+            for k in range(4):                                  # a, b, c, d
+                want = ref[k, :nk]
+                m = ~np.isnan(want)
+                assert np.abs(coef[m, col + k] - want[m]).max() < 1e-10
+
+
+def test_planner_outputs_match_the_reference(g):
+    p = params_from_golden(g, cport.frenet_params)
+    b = golden_batch(g, cport.spline_build)
+    out = cport.frenet_plan(b["coef"], b["knot_off"], b["path_id"], b["start"], b["ego_xy"], b["obs"], b["n_obs"], p)
+    assert np.array_equal(out["index"], g["index"])                          # selected candidate: exact
+    assert np.array_equal(out["n_valid"], g["n_valid"])                      # truncation at the end of the route
+    assert np.array_equal((out["flags"] & 1) != 0, g["feasible"])            # check_paths
+    assert np.array_equal((out["flags"] & 2) != 0, g["collision_free"])      # predict.check_collision
+    assert np.abs(out["cost"] - g["cost"]).max() / np.abs(g["cost"]).max() < 1e-12
+    m = ~np.isnan(g["x"])
+    assert np.array_equal(np.isnan(out["paths"][..., 0]), ~m)
+    assert np.abs(out["paths"][..., 0][m] - g["x"][m]).max() < 1e-9
+    assert np.abs(out["paths"][..., 1][m] - g["y"][m]).max() < 1e-9
+    tm = ~np.isnan(g["traj_xy"][..., 0])
+    assert np.array_equal(out["traj_len"], tm.sum(axis=1))
+    assert np.abs(out["traj"][..., 0][tm] - g["traj_xy"][..., 0][tm]).max() < 1e-9
+    assert np.abs(out["traj"][..., 1][tm] - g["traj_xy"][..., 1][tm]).max() < 1e-9
+    assert np.abs(out["traj"][..., 2] - g["traj_speed"]).max() < 1e-9        # zero speeds for index 0
+    assert (g["index"] == 0).sum() >= 3 and len(set(g["index"].tolist())) >= 4
+
+
+def test_near_tied_costs_are_reported_not_hidden(g):
+    """The last golden scenario starts (almost) on the lane centre: the +-d candidates differ in
+    cost by rounding only (~1e-13).  Which of two such candidates sorts first is decided by
+    LAPACK's rounding in the reference and is not restated; the oracle must agree on the costs to
+    that level and on the selected index (the centre candidate, unaffected by the tie)."""
+    c = g["cost"][-1]
+    assert abs(c[0] - c[8]) < 1e-9 and abs(c[1] - c[9]) < 1e-9
+    p = params_from_golden(g, cport.frenet_params)
+    b = golden_batch(g, cport.spline_build)
+    out = cport.frenet_plan(b["coef"], b["knot_off"], b["path_id"], b["start"], b["ego_xy"], b["obs"], b["n_obs"], p)
+    assert np.abs(out["cost"][-1] - c).max() < 1e-10 and out["index"][-1] == g["index"][-1] == 6
