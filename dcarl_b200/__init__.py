@@ -8,6 +8,7 @@ behind a C ABI (include/dcarl_b200.h, dcarl_b200/csrc/*.cu, bound in _abi.py wit
     Data_Generation, add_an_act_data, random_state_norm       data_sampling.py
     RLS, BoxBuffer                                            stable_baselines/deepq/RLS.py
     rollout_cv                                                constant-velocity surrogate
+    JunctionTrajectoryPlanner, frenet_plan, Routes            Agent/zzz/JunctionTrajectoryPlanner.py (+ predict.py)
 
 There is no CPU fallback: a compute call without the built library or without a CUDA device raises.
 """
@@ -18,6 +19,8 @@ from .sampling import (Data_Generation, add_an_act_data, generate, random_state_
                        random_state_norm, sample_returns, sample_returns_philox)
 from .rls import RLS, BoxBuffer, VISITED_STATE_DIST  # noqa: F401
 from .rollout import rollout_cv  # noqa: F401
+from .frenet import (FrenetParams, FrenetResult, JunctionTrajectoryPlanner, Routes, TrajectoryAction,  # noqa: F401
+                     dense_polyline2d, frenet_params, frenet_plan, frenet_state)
 from .io import load_rls_buffer, load_sim_data, save_rls_buffer  # noqa: F401
 from . import dist  # noqa: F401
 

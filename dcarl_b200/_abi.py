@@ -43,6 +43,21 @@ class RlsParams(C.Structure):
         super().__init__(rule_mean_gate, confidence_thres, visited_times_thres, min_candidate_visits)
 
 
+FRENET_MAX_D, FRENET_MAX_T, FRENET_MAX_V = 16, 4, 8
+
+
+class FrenetParams(C.Structure):
+    """dcarl_frenet_params — the sample grids and limits of JunctionTrajectoryPlanner.py:13-39."""
+    _fields_ = [("d_samples", C.c_double * FRENET_MAX_D), ("T_samples", C.c_double * FRENET_MAX_T),
+                ("tv_samples", C.c_double * FRENET_MAX_V), ("n_t", C.c_int32 * FRENET_MAX_T),
+                ("n_d", C.c_int32), ("n_T", C.c_int32), ("n_v", C.c_int32), ("n_pred", C.c_int32),
+                ("obstacles_considered", C.c_int32), ("pad_", C.c_int32),
+                ("dt", C.c_double), ("target_speed", C.c_double),
+                ("max_speed", C.c_double), ("max_accel", C.c_double), ("max_curvature", C.c_double),
+                ("robot_radius", C.c_double), ("move_gap", C.c_double),
+                ("kj", C.c_double), ("kt", C.c_double), ("kd", C.c_double), ("klat", C.c_double), ("klon", C.c_double)]
+
+
 _vp, _i32, _i64, _sz, _d, _f, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_double, C.c_float, C.c_uint64
 _int = C.c_int
 
@@ -69,6 +84,10 @@ SIGNATURES = {
     "dcarl_add_data_counts": (_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dcarl_add_data_rows": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _d, _vp, _vp, _vp]),
     "dcarl_rollout_cv": (_int, [_vp, _vp, _i64, _i32, _f, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "dcarl_default_frenet_params": (None, [C.POINTER(FrenetParams)]),
+    "dcarl_spline_build": (_int, [_vp, _vp, _i32, _vp, _vp]),
+    "dcarl_frenet_plan": (_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.POINTER(FrenetParams),
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -11,6 +11,8 @@
  *   DS  = Simulation_testing/Simulation_Data_Collection/Data_Sampling/data_sampling.py
  *   RLS = Field_testing/Software_and_Raw_Data_on_Self-Driving_Vehicle/software/src/tools/DCARL/
  *         stable_baselines/deepq/RLS.py
+ *   JTP / SPL / PRD = Simulation_testing/Simulation_Data_Collection/Data_From_Carla/Agent/zzz/
+ *         JunctionTrajectoryPlanner.py / cubic_spline_planner.py / predict.py
  *
  * Conventions
  *   - extern "C", plain pointers and sizes.  Unless a parameter says "host", every pointer is
@@ -181,6 +183,57 @@ int dcarl_rollout_cv(const float *state0, const int32_t *action, int64_t n, int3
                      float dt, float radius, float pass_x, const float *speed_scale,
                      int32_t n_actions, float *out_return, int32_t *out_steps, int32_t *out_term,
                      dcarl_stream_t stream);
+
+/* ---- "next" row f3: Frenet candidate trajectories + collision-checked selection --------------
+ * One planning tick of JunctionTrajectoryPlanner (JTP:103-140) for n independent scenarios.
+ *
+ * Routes.  A route is the cubic spline x(s), y(s) of SPL:123-178 through its knots (the densified
+ * lane centre line, JTP:79-90).  dcarl_spline_build turns P routes, knots concatenated as
+ * knots_xy float64 [K, 2] with route r owning rows [knot_off[r], knot_off[r+1]), into
+ * coef float64 [K, 9] rows {s, ax, bx, cx, dx, ay, by, cy, dy} (SPL:18-45; natural end conditions).
+ *
+ * Planning.  Scenario i runs on route path_id[i] from the Frenet start state
+ * start[i] = {s0, c_d, c_d_d, c_d_dd, c_speed} (JTP:248-276, 110) with obstacles
+ * obs[i, 0..n_obs[i]) = {x, y, vx, vy, yaw} (float64 [n, max_obs, 5]) and the ego position ego_xy[i]
+ * (only used to rank obstacles by distance, PRD:64-85).  Candidate c = (id*n_T + iT)*n_v + iv is the
+ * quintic d(t) to d_samples[id] and the quartic s(t) to speed tv_samples[iv] over T_samples[iT]
+ * (JTP:300-338); its points t = k*dt, k < n_t[iT], are mapped through the spline until one leaves
+ * the route (JTP:345-356).  Outputs, C = n_d*n_T*n_v <= 32, Tm = max n_t <= 32:
+ *   out_index [n]      0 = no admissible candidate (brake), c+1 = cheapest candidate that passes
+ *                      check_paths (JTP:381-394) and predict.check_collision (PRD:21-60); ties in
+ *                      cost go to the lower c, like sorted().  -1 = path_id out of range.
+ *   out_cost [n, C]    cf (JTP:333);  out_flags [n, C] bit0 = feasible, bit1 = collision-free
+ *   out_n_valid [n, C] points of the global path before it leaves the route
+ *   out_paths [n, C, Tm, 2] (nullable) global x, y; NaN past out_n_valid
+ *   out_traj [n, Tm, 3] x, y, desired speed of the selected trajectory (JTP:154-156); for index 0
+ *                      the cheapest candidate with zero speeds (JTP:149-150, the branch without a
+ *                      previous trajectory); out_traj_len [n] its number of valid points. */
+#define DCARL_FRENET_MAX_D 16
+#define DCARL_FRENET_MAX_T 4
+#define DCARL_FRENET_MAX_V 8
+typedef struct dcarl_frenet_params {
+    double d_samples[DCARL_FRENET_MAX_D];  /* JTP:300  np.arange(MAX_LEFT_WIDTH, MAX_RIGHT_WIDTH+1, D_ROAD_W) */
+    double T_samples[DCARL_FRENET_MAX_T];  /* JTP:303  np.arange(MINT, MAXT, DT) */
+    double tv_samples[DCARL_FRENET_MAX_V]; /* JTP:315  np.arange(target - D_T_S*N, target + D_T_S*N, D_T_S) */
+    int32_t n_t[DCARL_FRENET_MAX_T];       /* JTP:308  len(np.arange(0, Ti, DT)) */
+    int32_t n_d, n_T, n_v;
+    int32_t n_pred;                        /* PRD:91   len(np.arange(0, MAXT, DT)) */
+    int32_t obstacles_considered;          /* JTP:28   4 */
+    int32_t pad_;
+    double dt;                             /* JTP:19   0.3 */
+    double target_speed;                   /* JTP:22   30/3.6 */
+    double max_speed, max_accel, max_curvature; /* JTP:13-15 */
+    double robot_radius, move_gap;         /* JTP:29, 31 */
+    double kj, kt, kd, klat, klon;         /* JTP:35-39 */
+} dcarl_frenet_params;
+void dcarl_default_frenet_params(dcarl_frenet_params *p);   /* host pointer; the shipped constants */
+int dcarl_spline_build(const double *knots_xy, const int64_t *knot_off, int32_t n_paths, double *coef,
+                       dcarl_stream_t stream);
+int dcarl_frenet_plan(const double *coef, const int64_t *knot_off, int32_t n_paths, const int32_t *path_id,
+                      const double *start, const double *ego_xy, const double *obs, const int32_t *n_obs,
+                      int32_t max_obs, int64_t n, const dcarl_frenet_params *p /* host */,
+                      int32_t *out_index, double *out_cost, uint8_t *out_flags, int32_t *out_n_valid,
+                      double *out_paths, double *out_traj, int32_t *out_traj_len, dcarl_stream_t stream);
 
 #ifdef __cplusplus
 }

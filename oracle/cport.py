@@ -213,6 +213,8 @@ def frenet_plan(coef, knot_off, path_id, start, ego_xy, obs, n_obs, params, want
     max_obs = obs.shape[1]
     Cn = params.n_d * params.n_T * params.n_v
     Tm = max(params.n_t[:params.n_T])
+    if Cn > 32 or Tm > 32 or max_obs > 16:
+        raise ValueError("oracle: at most 32 candidates, 32 points per path, 16 obstacles per scenario")
     out = dict(index=np.empty(n, np.int32), cost=np.empty((n, Cn)), flags=np.empty((n, Cn), np.uint8),
                n_valid=np.empty((n, Cn), np.int32), paths=np.empty((n, Cn, Tm, 2)) if want_paths else None,
                traj=np.empty((n, Tm, 3)), traj_len=np.empty(n, np.int32))

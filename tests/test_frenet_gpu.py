@@ -1,0 +1,140 @@
+"""Parity of the CUDA Frenet planner (through the C ABI) with the reference's golden outputs and
+with the oracle.  Selected index, feasibility / collision flags and truncation lengths are exact;
+costs, paths and spline coefficients within 1e-9 (float64)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import dcarl_b200 as dc
+from dcarl_b200 import frenet as fr
+from oracle import cport
+from helpers_frenet import golden_batch, params_from_golden, synth_routes, synth_scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g(golden):
+    return golden("frenet")
+
+
+def _routes_from(batch):
+    off = batch["knot_off"]
+    return fr.Routes([batch["knots"][off[i]:off[i + 1]] for i in range(len(off) - 1)])
+
+
+def test_spline_build_matches_the_reference_coefficients(g):
+    b = golden_batch(g)
+    routes = _routes_from(b)
+    for i in range(int(g["n_cases"])):
+        coef = routes.coefficients(i)
+        nk = int(g["n_knots"][i])
+        assert np.abs(coef[:, 0] - g["spline_s"][i, :nk]).max() < 1e-12
+        for col, ref in ((1, g["spline_cx"][i]), (5, g["spline_cy"][i])):
+            for k in range(4):
+                want = ref[k, :nk]
+                m = ~np.isnan(want)
+                assert np.abs(coef[m, col + k] - want[m]).max() < 1e-10
+
+
+def test_plan_matches_the_reference_run(g):
+    p = params_from_golden(g, fr.frenet_params)
+    b = golden_batch(g)
+    res = fr.frenet_plan(_routes_from(b), b["path_id"], b["start"], b["ego_xy"], b["obs"], b["n_obs"], p, want_paths=True)
+    assert np.array_equal(res.index, g["index"])
+    assert np.array_equal(res.n_valid, g["n_valid"])
+    assert np.array_equal(res.feasible, g["feasible"])
+    assert np.array_equal(res.collision_free, g["collision_free"])
+    assert np.abs(res.cost - g["cost"]).max() / np.abs(g["cost"]).max() < 1e-12
+    m = ~np.isnan(g["x"])
+    assert np.array_equal(np.isnan(res.paths[..., 0]), ~m)
+    assert np.abs(res.paths[..., 0][m] - g["x"][m]).max() < 1e-9
+    assert np.abs(res.paths[..., 1][m] - g["y"][m]).max() < 1e-9
+    tm = ~np.isnan(g["traj_xy"][..., 0])
+    assert np.array_equal(res.traj_len, tm.sum(axis=1))
+    assert np.abs(res.traj[..., 0][tm] - g["traj_xy"][..., 0][tm]).max() < 1e-9
+    assert np.abs(res.traj[..., 1][tm] - g["traj_xy"][..., 1][tm]).max() < 1e-9
+    assert np.abs(res.traj[..., 2] - g["traj_speed"]).max() < 1e-9
+
+
+def _against_oracle(n, n_paths, seed, params_kw=None, max_obs=6):
+    rng = np.random.default_rng(seed)
+    knots, off = synth_routes(rng, n_paths)
+    pid, start, ego, obs, n_obs = synth_scenarios(rng, n, knots, off, max_obs=max_obs)
+    kw = params_kw or {}
+    po, pg = cport.frenet_params(**kw), fr.frenet_params(**kw)
+    coef = np.concatenate([cport.spline_build(knots[off[i]:off[i + 1]]) for i in range(n_paths)])
+    ref = cport.frenet_plan(coef, off, pid, start, ego, obs, n_obs, po)
+    routes = fr.Routes([knots[off[i]:off[i + 1]] for i in range(n_paths)])
+    assert np.abs(routes.coef.cpu().numpy() - coef).max() < 1e-9
+    res = fr.frenet_plan(routes, pid, start, ego, obs, n_obs, pg, want_paths=True)
+    flags = res.feasible.astype(np.uint8) | (res.collision_free.astype(np.uint8) << 1)
+    # a flag can only differ where a limit is met to within rounding; none is expected
+    assert np.array_equal(flags, ref["flags"]), f"{(flags != ref['flags']).sum()} flag mismatches"
+    assert np.array_equal(res.index, ref["index"])
+    assert np.array_equal(res.n_valid, ref["n_valid"]) and np.array_equal(res.traj_len, ref["traj_len"])
+    assert np.abs(res.cost - ref["cost"]).max() / np.abs(ref["cost"]).max() < 1e-11
+    m = ~np.isnan(ref["paths"])
+    assert np.array_equal(np.isnan(res.paths), ~m)
+    assert np.abs(res.paths[m] - ref["paths"][m]).max() < 1e-8
+    tm = ~np.isnan(ref["traj"])
+    assert np.array_equal(np.isnan(res.traj), ~tm) and np.abs(res.traj[tm] - ref["traj"][tm]).max() < 1e-8
+    return res
+
+
+def test_random_scenarios_vs_oracle():
+    res = _against_oracle(6000, 37, seed=11)
+    hist = np.bincount(res.index, minlength=11)
+    assert hist[0] > 0 and (hist[1:] > 0).sum() >= 4          # brake and several different candidates occur
+    assert (~res.collision_free).any() and (~res.feasible).any() and (res.n_valid < 14).any()
+
+
+def test_other_grids_and_limits_vs_oracle():
+    # 7 offsets x 2 horizons x 2 speeds = 28 candidates, 14- and 15-point paths, tighter limits, 2 obstacles considered
+    _against_oracle(1500, 9, seed=12, params_kw=dict(MAX_LEFT_WIDTH=-3, MAX_RIGHT_WIDTH=3, D_ROAD_W=1, MINT=4.0, MAXT=4.5,
+                                                      MAX_SPEED=11.0, MAX_ACCEL=2.0, MAX_CURVATURE=0.5,
+                                                      OBSTACLES_CONSIDERED=2, ROBOT_RADIUS=2))
+    _against_oracle(700, 5, seed=13, params_kw=dict(N_S_SAMPLE=2, D_T_S=5 / 3.6, KD=3.0, KJ=0.3), max_obs=12)
+
+
+def test_device_tensors_no_obstacles_and_bad_route_id():
+    rng = np.random.default_rng(5)
+    knots, off = synth_routes(rng, 3)
+    routes = fr.Routes([knots[off[i]:off[i + 1]] for i in range(3)])
+    pid, start, ego, obs, n_obs = synth_scenarios(rng, 64, knots, off, max_obs=4)
+    dv = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+    res = fr.frenet_plan(routes, dv(pid, torch.int32), dv(start, torch.float64), dv(ego, torch.float64),
+                         dv(obs, torch.float64), dv(np.zeros_like(n_obs), torch.int32))
+    assert res.index.is_cuda and bool(res.collision_free.all())             # no obstacles: nothing collides (PRD:23-24)
+    host = fr.frenet_plan(routes, pid, start, ego, obs, np.zeros_like(n_obs))
+    assert np.array_equal(host.index, res.index.cpu().numpy())
+    bad = pid.copy()
+    bad[7] = 3
+    with pytest.raises(IndexError):
+        fr.frenet_plan(routes, bad, start, ego, obs, n_obs)
+    empty = fr.frenet_plan(routes, np.zeros(0, np.int32), np.zeros((0, 5)), np.zeros((0, 2)), np.zeros((0, 1, 5)), np.zeros(0, np.int32))
+    assert empty.index.shape == (0,)
+    with pytest.raises(dc.DcarlError):
+        fr.frenet_plan(routes, pid, start, ego, obs, n_obs, fr.frenet_params(D_ROAD_W=1, MAX_LEFT_WIDTH=-7, MAX_RIGHT_WIDTH=7, N_S_SAMPLE=2))   # 60 candidates
+
+
+def test_drop_in_planner_class_reproduces_the_reference_tick(g):
+    NS = types.SimpleNamespace
+    for i in (0, 5, 17, 21, 40, 52, 63):
+        nl = int(g["n_lane"][i])
+        lane = [NS(position=NS(x=float(x), y=float(y))) for x, y in g["lane_xy"][i, :nl]]
+        no = int(g["n_obs"][i])
+        veh = [NS(x=o[0], y=o[1], vx=o[2], vy=o[3], yaw=o[4]) for o in g["obs"][i, :no]]
+        ego = NS(x=float(g["ego_xy"][i, 0]), y=float(g["ego_xy"][i, 1]), vx=float(g["ego_v"][i, 0]),
+                 vy=float(g["ego_v"][i, 1]), v=float(g["ego_v"][i, 2]))
+        dm = NS(ego_vehicle=ego, vehicles=veh, lanes=[NS(central_path=lane)], lanes_updated=False)
+        planner = dc.JunctionTrajectoryPlanner()
+        action, index = planner.trajectory_update(dm)
+        assert index == int(g["index"][i])
+        n = int((~np.isnan(g["traj_xy"][i, :, 0])).sum())
+        assert action.trajectory.shape == (n, 2)
+        assert np.abs(action.trajectory - g["traj_xy"][i, :n]).max() < 1e-8
+        assert np.abs(np.array(action.desired_speed) - g["traj_speed"][i]).max() < 1e-8
+        assert len(planner.all_trajectory) == g["cost"].shape[1]

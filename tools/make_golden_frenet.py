@@ -95,6 +95,8 @@ def run_one(dm):
         spline_cy=np.stack([pl.csp.sy.a, np.r_[pl.csp.sy.b, np.nan], pl.csp.sy.c, np.r_[pl.csp.sy.d, np.nan]]),
         start=np.array([st.s0, st.c_d, st.c_d_d, st.c_d_dd, pl.c_speed]),
         ego_xy=np.array([dm.ego_vehicle.x, dm.ego_vehicle.y]),
+        ego_v=np.array([dm.ego_vehicle.vx, dm.ego_vehicle.vy, dm.ego_vehicle.v]),
+        lane_xy=np.array([[q.position.x, q.position.y] for q in dm.lanes[0].central_path]),
         obs=np.array([[v.x, v.y, v.vx, v.vy, v.yaw] for v in dm.vehicles]).reshape(-1, 5),
         cost=np.array([c[1] for c in cands]),
         n_valid=np.array([len(c[0].x) for c in cands]),
@@ -159,8 +161,10 @@ def main():
     pack["spline_cx"] = np.stack([np.pad(c["spline_cx"], ((0, 0), (0, nk - c["spline_cx"].shape[1])), constant_values=np.nan) for c in cases])
     pack["spline_cy"] = np.stack([np.pad(c["spline_cy"], ((0, 0), (0, nk - c["spline_cy"].shape[1])), constant_values=np.nan) for c in cases])
     pack["obs"] = pad("obs", no)
+    pack["lane_xy"] = pad("lane_xy", max(len(c["lane_xy"]) for c in cases))
+    pack["n_lane"] = np.array([len(c["lane_xy"]) for c in cases])
     pack["n_obs"] = np.array([len(c["obs"]) for c in cases])
-    for k in ("start", "ego_xy", "cost", "n_valid", "x", "y", "s", "d", "s_d", "s_dd", "feasible", "collision_free",
+    for k in ("start", "ego_xy", "ego_v", "cost", "n_valid", "x", "y", "s", "d", "s_d", "s_dd", "feasible", "collision_free",
               "index", "traj_xy", "traj_speed", "route", "n_pred"):
         pack[k] = np.stack([np.asarray(c[k]) for c in cases])
     # the module constants the run used (JunctionTrajectoryPlanner.py:13-41)
