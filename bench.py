@@ -388,7 +388,89 @@ def secondary(dev, peak):
     _, steps_run, _ = dc.rollout_cv(s0, ra)
     out["rollout_cv"] = {"episodes": ne, "ms": ms, "kinematic_steps_per_s": float(steps_run.sum()) / (ms * 1e-3),
                          "episodes_per_s": ne / (ms * 1e-3), "note": "96 B per episode: latency/compute bound, no roofline fraction"}
+    del s0, ra, zs, zr, ac
+    out["frenet_plan"] = frenet_leg(dev)
     return out
+
+
+def synth_frenet(n, n_paths, seed, max_obs=4):
+    """Planner inputs for the Frenet leg: gently curved lanes with 2 m knots, a start state along a
+    random lane, slow obstacles on the corridor ahead (vectorised numpy; same recipe as the tests)."""
+    rng = np.random.default_rng(seed)
+    knots, off = [], [0]
+    for _ in range(n_paths):
+        L = rng.uniform(80, 220)
+        sk = np.linspace(0, L, int(round(L / 2)))
+        amp, w, ph, th = rng.uniform(0, 8), rng.uniform(15, 60), rng.uniform(0, 6.28), rng.uniform(-3.14, 3.14)
+        x, y = sk, amp * np.sin(sk / w + ph)
+        knots.append(np.stack([x * np.cos(th) - y * np.sin(th), x * np.sin(th) + y * np.cos(th)], 1) + rng.uniform(-100, 100, 2))
+        off.append(off[-1] + len(sk))
+    off = np.array(off, np.int64)
+    pid = rng.integers(0, n_paths, n).astype(np.int32)
+    nk = (off[1:] - off[:-1])[pid]
+    j = (off[:-1][pid] + (rng.uniform(0.02, 0.7, n) * (nk - 2)).astype(np.int64))
+    allk = np.concatenate(knots)
+    u = allk[j + 1] - allk[j]
+    seglen = np.hypot(u[:, 0], u[:, 1])
+    u /= seglen[:, None]
+    nrm = np.stack([-u[:, 1], u[:, 0]], 1)
+    c_d = rng.uniform(-3, 3, n)
+    s0 = (j - off[:-1][pid]) * 2.0 + 1.0                       # knots are ~2 m apart
+    start = np.stack([s0, c_d, rng.normal(0, 0.4, n), np.zeros(n), rng.uniform(0.2, 12.0, n)], 1)
+    ego = allk[j] + u * 1.0 + nrm * c_d[:, None]
+    ahead, side = rng.uniform(2, 30, (n, max_obs)), rng.uniform(-5, 5, (n, max_obs))
+    pos = ego[:, None, :] + u[:, None, :] * ahead[..., None] + nrm[:, None, :] * (side - c_d[:, None])[..., None]
+    v, yaw = rng.uniform(0, 2, (n, max_obs)), rng.uniform(-3.14, 3.14, (n, max_obs))
+    obs = np.concatenate([pos, (v * np.cos(yaw))[..., None], (v * np.sin(yaw))[..., None], yaw[..., None]], 2)
+    n_obs = rng.integers(0, max_obs + 1, n).astype(np.int32)
+    return knots, off, pid, start, ego, obs, n_obs
+
+
+def frenet_leg(dev):
+    """SURVEY row f3 at BASELINE config-5's scenario count: one planning tick (10 candidates x 14
+    points, collision-checked pick) for 262 144 scenarios per launch, device-resident inputs; the
+    oracle's C restatement of the reference planner on the host cores beside it, on a sample."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    import dcarl_b200 as dc
+    from oracle import cport
+    n, n_paths = 262144, 64
+    knots, off, pid, start, ego, obs, n_obs = synth_frenet(n, n_paths, 5000)
+    routes = dc.Routes(knots)
+    p = dc.frenet_params()
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    d = (t(pid, torch.int32), t(start, torch.float64), t(ego, torch.float64), t(obs, torch.float64), t(n_obs, torch.int32))
+    res = dc.frenet_plan(routes, *d, p)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        res = dc.frenet_plan(routes, *d, p)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    C, T = p.n_d * p.n_T * p.n_v, max(p.n_t[:p.n_T])
+    # CPU: the oracle on a sample, all cores (ctypes releases the GIL)
+    cores = _cores()
+    ns = min(n, 8192 * cores)
+    coef = np.concatenate([cport.spline_build(k) for k in knots])
+    po = cport.frenet_params()
+    parts = np.array_split(np.arange(ns), cores)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        outs = list(ex.map(lambda q: cport.frenet_plan(coef, off, pid[q], start[q], ego[q], obs[q], n_obs[q], po, want_paths=False)["index"], parts))
+    dt = time.perf_counter() - t0
+    cpu_idx = np.concatenate(outs)
+    gpu_idx = res.index[:ns].cpu().numpy()
+    return {"scenarios": n, "candidates": C, "points_per_candidate": T, "ms": ms, "scenarios_per_s": n / (ms * 1e-3),
+            "candidate_points_per_s": n * C * T / (ms * 1e-3),
+            "io_bytes_per_scenario": 5 * 8 + 2 * 8 + obs.shape[1] * 40 + 8 + 4 + C * 13 + T * 24 + 4,
+            "selected_index_histogram": np.bincount(res.index.cpu().numpy(), minlength=C + 1).tolist(),
+            "cpu_oracle": {"scenarios_per_s": ns / dt, "cores": cores, "sample": f"{ns} scenarios, C restatement of the reference planner, {dt:.2f} s"},
+            "index_mismatches_vs_cpu_sample": int((cpu_idx != gpu_idx).sum()),
+            "note": "compute-bound float64 (one warp per scenario): no bandwidth roofline; the reference's Python planner "
+                    "takes ~10 ms per scenario per core (measured in the build container, not on this box)"}
 
 
 def cpu_legs(plan, idx, act, R):
