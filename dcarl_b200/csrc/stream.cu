@@ -143,6 +143,31 @@ __device__ __forceinline__ void warp_top2(const double *row, int stride, int A, 
     second = shfl_f64(contrib, __ffs(win2) - 1);
 }
 
+// Inverse of order_key.
+__device__ __forceinline__ double key_to_double(unsigned hi, unsigned lo) {
+    const unsigned sgn = ~(unsigned)((int)hi >> 31);   // key top bit clear <=> the double was negative
+    return __hiloint2double((int)(hi ^ (sgn | 0x80000000u)), (int)(lo ^ sgn));
+}
+
+// A <= 32: one action per lane.  Exact (max, first argmax, max of the rest) with four integer
+// reductions; lanes past A hold -inf, so a single action gives second = -inf.
+__device__ __forceinline__ void warp_top2_small(const double *row, int stride, int A, double &mx, int &arg,
+                                                double &second) {
+    const int lane = lane_id();
+    const double c = lane < A ? row[(size_t)lane * stride] : -CUDART_INF;
+    unsigned hi, lo;
+    order_key(c, hi, lo);
+    const unsigned H = __reduce_max_sync(FULL_MASK, hi);
+    const bool top = hi == H;
+    const unsigned L = __reduce_max_sync(FULL_MASK, top ? lo : 0u);
+    arg = __ffs(__ballot_sync(FULL_MASK, top && lo == L)) - 1;
+    mx = key_to_double(H, L);
+    const bool rest = lane != arg;
+    const unsigned H2 = __reduce_max_sync(FULL_MASK, rest ? hi : 0u);
+    const unsigned L2 = __reduce_max_sync(FULL_MASK, (rest && hi == H2) ? lo : 0u);
+    second = key_to_double(H2, L2);
+}
+
 struct Cell {
     double s1, s2, val;
 };
@@ -191,7 +216,7 @@ __device__ __forceinline__ void peer_masks(int s, int a, unsigned &ms, unsigned 
 __device__ unsigned long long g_rows_timing[4 * 65536];   // per instance: start ns, end ns, smid, hw warp id
 #endif
 
-template <typename RT, typename OT, bool OVERALL>
+template <typename RT, typename OT, bool OVERALL, bool FORCE_FIRST>
 __global__ void __launch_bounds__(kRowsMaxWarps * 32, 1)
 k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -254,7 +279,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     const unsigned ebase = (unsigned)inst * n_steps + lane;
 
     double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
-    unsigned bad = 0;     // lane-local count of out-of-range rows
+    unsigned max_idx = 0, max_act = 0;   // lane-local maxima of the raw keys: out-of-range rows show up here
 
     int n_idx = 0, n_act = 0;
     RT n_R = RT(0);
@@ -272,10 +297,11 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         RT rin, r1, r2;     // own return and those of the two oldest earlier peers
     };
     struct Sel {       // selector stage results
-        double m_out, mprev_out;
-        int g_out, ast;
-        unsigned need;
-        bool any_need;
+        double m_out, mprev_out;   // the state's max just after / just before the row
+        int g_out;                 // the state's argmax after the row
+        bool act_prev;             // the row's state was activated before the row
+        bool jump;                 // the row activates its state (ST1:98-99)
+        bool any_jump;             // warp-uniform: some row of the batch does
     };
 
     // ---- moment stage, issue part: consume the prefetched rows, request the batch after, start
@@ -285,9 +311,12 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     auto p1a_issue = [&](auto tail_tag, const unsigned k, Rows &r, Mom &m) {
         constexpr bool TAIL = decltype(tail_tag)::value;
         const bool in_stream = TAIL ? (k < n_steps) : true;
+        // out-of-range keys are clamped (memory safety) and remembered: the call then reports bad rows
+        // (lanes past the end of the stream re-read keys that were already checked)
         const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
         const int a = (int)min((unsigned)n_act, (unsigned)(A - 1));
-        if (in_stream && (s_in != n_idx || a != n_act)) bad++;
+        max_idx = max(max_idx, (unsigned)n_idx);
+        max_act = max(max_act, (unsigned)n_act);
         m.rin = n_R;
         const unsigned e = ebase + (k - lane);
         if (k + 32 < n_steps) { n_idx = ld_stream(gidx + e + 32); n_act = ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
@@ -350,8 +379,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         const double v = r.v;
         const int a = r.a;
         const unsigned ms = r.ms, mk = r.mk;
-        o.ast = ga.actstep;
         o.m_out = 0.0; o.mprev_out = 0.0; o.g_out = -1;
+        o.act_prev = false; o.jump = false; o.any_jump = false;
         unsigned pend = __ballot_sync(FULL_MASK, r.active);
         bool mine = r.active;
         unsigned fm, fin;
@@ -370,17 +399,21 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const bool gt_ub = v > c_ub, le_ub = v <= c_ub, lt_mk = v < m_k;
             const bool doubt = mine & upd & (T ? !gt_ub : !(le_ub & lt_mk));
             const bool lift = doubt & !T & lt_mk & ((ms & gt) == 0);
-            fm = __ballot_sync(FULL_MASK, doubt & !lift);
+            // FORCE_FIRST (the priors' argmax is not the rule action): every row of a state that is
+            // not activated yet goes through the exact path, which is where activation is recorded
+            const bool forced = FORCE_FIRST ? (mine & (ga.actstep == -1)) : false;
+            fm = __ballot_sync(FULL_MASK, (doubt & !lift) | forced);
             fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;
             __syncwarp();
             const bool done = mine & ((fin & bit) != 0);
             o.g_out = done ? c_g : o.g_out;
             o.m_out = done ? m_k : o.m_out;
             o.mprev_out = done ? m_prev : o.mprev_out;
+            o.act_prev = done ? (ga.actstep != -1) : o.act_prev;
             if (done & upd & ((mk & fin & gt) == 0)) cell->val = v;
             if (done & ((ms & fin & gt) == 0)) sh->smax = m_k;
             if (__any_sync(FULL_MASK, lift)) {   // rare
-                if (done & lift) sh->sub2 = runner_up_bound(v, m_k);
+                if (done & lift & !forced) sh->sub2 = runner_up_bound(v, m_k);
             }
         };
         round();
@@ -391,19 +424,31 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 __syncwarp();
                 const int sj = __shfl_sync(FULL_MASK, r.s, j);
                 const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
-                if (lane_ == j) cell->val = v;
+                if (lane_ == j && upd) cell->val = v;
                 __syncwarp();
-                const int old_g = sargs[sj].sarg;
+                const StateArg oa = sargs[sj];
                 double mx, second; int arg;
-                warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
-                if (arg != old_g) {
+                if (A <= 32) warp_top2_small(&cells[sj * A].val, 3, A, mx, arg, second);
+                else warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
+                // The argmax only ever changes here, so a state can only activate here (ST1:98-99):
+                // between two exact rows "argmax != rule" implies "already activated".
+                const bool activates = oa.actstep == -1 && arg != rule;
+                if (arg != oa.sarg || activates) {
                     unsigned csum = 0;
                     for (int q = lane_; q < A; q += 32) csum += cnt[sj * A + q];
+                    // 1-based count of this state's rows up to and including row j
                     const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
-                    if (lane_ == j) { hist[old_g] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1; }
+                    if (lane_ == j) {
+                        if (arg != oa.sarg) {
+                            // rows (flushpt, t_j) of this state were emitted with the old argmax: account for them
+                            hist[oa.sarg] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1;
+                        }
+                        if (activates) { sa->actstep = t_j; o.jump = true; }
+                    }
+                    o.any_jump |= activates;
                 }
                 if (lane_ == j) {
-                    o.g_out = arg; o.m_out = mx; o.mprev_out = m_prev;
+                    o.g_out = arg; o.m_out = mx; o.mprev_out = m_prev; o.act_prev = oa.actstep != -1;
                     sh->smax = mx; sh->sub2 = runner_up_bound(second, mx); sa->sarg = arg;
                 }
                 __syncwarp();
@@ -414,18 +459,6 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 ga = *sa;
                 round();
                 if (fm == 0) break;
-            }
-        }
-        // ---- activation step (ST1:98-99): first row of a state whose argmax is not the rule action
-        o.need = __ballot_sync(FULL_MASK, r.active && o.ast == -1 && o.g_out != rule);
-        o.any_need = o.need != 0;                                                  // warp-uniform
-        o.need &= ms;
-        if (o.any_need) {   // rare: once per state
-            __syncwarp();
-            if (o.need && lane_ == __ffs(o.need) - 1) {
-                unsigned csum = 0;
-                for (int q = 0; q < A; ++q) csum += cnt[r.sx * A + q];
-                sa->actstep = (int)csum - __popc(ms & gt);   // 1-based count of this state's rows up to here
             }
         }
     };
@@ -440,10 +473,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             st_stream(oact + e, o.g_out);
         }
         if (OVERALL) {
-            const bool act_before = o.ast != -1;
             // rows of states that were active before the row: the bonus cancels in after - before
-            const bool act_prev = act_before || (o.need & lt) != 0;
-            const double d = (r.active && act_prev) ? o.m_out - o.mprev_out : 0.0;
+            const double d = (r.active && o.act_prev) ? o.m_out - o.mprev_out : 0.0;
             double pre;
             if constexpr (SCAN_F32) {
                 float f = (float)d;
@@ -461,8 +492,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                     if (lane >= off) pre += q;
                 }
             }
-            if (o.any_need) {   // rare: a state activates at this row, its (max + bonus) enters the sum
-                double jmp = (r.active && !act_prev && (o.need & le) != 0) ? o.m_out + bonus : 0.0;
+            if (o.any_jump) {   // rare: a state activates at this row, its (max + bonus) enters the sum
+                double jmp = o.jump ? o.m_out + bonus : 0.0;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
                     const double q = __shfl_up_sync(FULL_MASK, jmp, off);
@@ -532,7 +563,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         for (int a = lane; a < A; a += 32)
             if (hist[a]) atomicAdd(p.act_hist + a, (unsigned long long)hist[a]);
     }
-    if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, (unsigned long long)bad);
+    if (p.bad_rows != nullptr && (max_idx >= (unsigned)S || max_act >= (unsigned)A)) atomicAdd(p.bad_rows, 1ull);
 }
 
 // ---- general-shape walker: tables in global memory, one row at a time ----------------------
@@ -713,12 +744,21 @@ static int pick_warps_per_cta(long long n_inst, size_t wb, int sms) {
     return (int)(fit < 4 ? fit : 4);
 }
 
-template <typename RT, typename OT, bool OV>
-static int launch_rows(const StreamArgs &a, cudaStream_t st) {
+// The argmax of the priors (ST1:51-53): when it is not the rule action, every state activates on its
+// first row without any change of argmax, which the kernel handles by forcing those rows through its
+// exact path (FORCE_FIRST).
+static bool priors_argmax_is_rule(const StreamArgs &a) {
+    if (a.prior_rule > a.prior_other) return true;
+    if (a.prior_rule == a.prior_other) return a.rule_act == 0;
+    return a.A == 1;
+}
+
+template <typename RT, typename OT, bool OV, bool FF>
+static int launch_rows_ff(const StreamArgs &a, cudaStream_t st) {
     const size_t wb = rows_warp_bytes(a.S, a.A);
     const int wpc = pick_warps_per_cta(a.n_inst, wb, sm_count());
     const size_t smem = kRowsCtaFixedBytes + wb * wpc;
-    auto kern = k_stream_rows<RT, OT, OV>;
+    auto kern = k_stream_rows<RT, OT, OV, FF>;
     static size_t configured = 0;   // per template instance; growing only
     if (smem > configured) {
         DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
@@ -741,6 +781,11 @@ static int launch_rows(const StreamArgs &a, cudaStream_t st) {
         DCARL_LAUNCH_CHECK("k_stream_rows");
     }
     return 0;
+}
+
+template <typename RT, typename OT, bool OV>
+static int launch_rows(const StreamArgs &a, cudaStream_t st) {
+    return priors_argmax_is_rule(a) ? launch_rows_ff<RT, OT, OV, false>(a, st) : launch_rows_ff<RT, OT, OV, true>(a, st);
 }
 
 template <typename RT, typename OT, bool OV>

@@ -85,9 +85,9 @@ int dcarl_bounds(const void *x, int x_is_f64, const int64_t *seg_offsets, int64_
  *   out_overall[i,k] (nullable) = sum over activated states of (max + activation_bonus), ST2:99-105
  *   out_activation_step[i,s] = per-state 1-based step at which argmax first left rule_act, else -1
  *   act_hist[A] (nullable, uint64, ACCUMULATED into) = histogram of out_act over all rows.
- * Rows with idx/act out of range are an input error (the reference raises IndexError): they are
- * counted in *bad_rows (nullable, uint64, accumulated), never index out of bounds, and leave the
- * outputs of their instance unspecified; callers must treat *bad_rows != 0 as a failed call.
+ * Rows with idx/act out of range are an input error (the reference raises IndexError): they never
+ * index out of bounds, leave the outputs of their instance unspecified, and make *bad_rows
+ * (nullable, uint64, accumulated) non-zero; callers must treat *bad_rows != 0 as a failed call.
  * variant: 0 = default (row-parallel shared-memory kernel when the S*A table fits in shared
  * memory, else the global-memory walker), 1 = force the walker (needs ws), 2 = force the
  * row-parallel kernel (error if it does not fit).

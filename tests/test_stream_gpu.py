@@ -58,6 +58,11 @@ SHAPES = [
     (4, 600, 2, 3, {"alpha": 0.2, "scale": 40.0, "cap": 60.0, "activation_bonus": 2.5}),
     (3, 4000, 30, 256, {}),                      # config-4-sized action set: 7680 cells, one instance per CTA
     (2, 300, 1, 1, {}),                          # a single cell
+    # the priors' argmax is not the rule action: every state activates on its first row
+    (6, 800, 4, 6, {"rule_act": 3, "prior_other": 100.0}),
+    (6, 800, 4, 6, {"prior_rule": -80.0}),
+    (6, 800, 4, 6, {"prior_rule": -80.0, "n_thres": 0}),
+    (5, 700, 3, 40, {"rule_act": 2, "prior_other": 100.0}),
 ]
 
 
