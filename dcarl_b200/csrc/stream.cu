@@ -264,6 +264,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
 #endif
     const unsigned bit = 1u << lane;
     const unsigned lt = bit - 1u, le = lt | bit, gt = ~le;
+    auto gt_of = [](int l) { return ~((2u << l) - 1u); };   // lanes strictly above lane l
     const unsigned n_steps = p.n_steps;
     const double c_h = p.c_h, cap = p.cap, bonus = p.bonus;
     const int rule = p.rule_act;
@@ -395,14 +396,27 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const double vp = shfl_f64(v, jp);
             m_prev = cand ? vp : c_ms0;
             const double m_k = T ? v : m_prev;
-            // (bitwise on purpose: all three compares are evaluated, no short-circuit branches)
-            const bool gt_ub = v > c_ub, le_ub = v <= c_ub, lt_mk = v < m_k;
-            const bool doubt = mine & upd & (T ? !gt_ub : !(le_ub & lt_mk));
-            const bool lift = doubt & !T & lt_mk & ((ms & gt) == 0);
-            // FORCE_FIRST (the priors' argmax is not the rule action): every row of a state that is
-            // not activated yet goes through the exact path, which is where activation is recorded
+            // (bitwise on purpose: the compares are evaluated unconditionally, no short-circuit branches)
+            const bool gt_ub = v > c_ub, lt_mk = v < m_k;
+            // A row of another cell that rises above the runner-up bound but stays below the max keeps
+            // the argmax; it only lifts the bound that later argmax-cell rows of its state must clear.
             const bool forced = FORCE_FIRST ? (mine & (ga.actstep == -1)) : false;
-            fm = __ballot_sync(FULL_MASK, (doubt & !lift) | forced);
+            const bool lifter = mine & upd & !T & gt_ub & lt_mk & !forced;
+            const unsigned lm = __ballot_sync(FULL_MASK, lifter);
+            double B = c_ub;   // bound in force at this row: c_ub and the earlier lifters of its state
+            if (lm != 0) {     // rare
+                for (unsigned w = lm; w; w &= w - 1) {
+                    const int l = __ffs(w) - 1;
+                    const double vl = shfl_f64(v, l);
+                    const unsigned msl = __shfl_sync(FULL_MASK, ms, l);
+                    if ((msl & bit & gt_of(l)) && vl > B) B = vl;
+                }
+            }
+            // doubtful: the argmax cell drops to the bound, or another cell reaches the max.
+            // FORCE_FIRST (the priors' argmax is not the rule action): every row of a state that is
+            // not activated yet goes through the exact path, which is where activation is recorded.
+            const bool doubt = mine & upd & (T ? !(v > B) : !lt_mk);
+            fm = __ballot_sync(FULL_MASK, doubt | forced);
             fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;
             __syncwarp();
             const bool done = mine & ((fin & bit) != 0);
@@ -411,9 +425,10 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             o.mprev_out = done ? m_prev : o.mprev_out;
             o.act_prev = done ? (ga.actstep != -1) : o.act_prev;
             if (done & upd & ((mk & fin & gt) == 0)) cell->val = v;
-            if (done & ((ms & fin & gt) == 0)) sh->smax = m_k;
-            if (__any_sync(FULL_MASK, lift)) {   // rare
-                if (done & lift & !forced) sh->sub2 = runner_up_bound(v, m_k);
+            const bool last_of_state = done & ((ms & fin & gt) == 0);
+            if (last_of_state) sh->smax = m_k;
+            if (lm != 0) {     // rare: the last finalized row of a lifted state re-centres its bound
+                if (last_of_state & ((lm & ms & fin) != 0)) sh->sub2 = runner_up_bound((lifter & (v > B)) ? v : B, m_k);
             }
         };
         round();
