@@ -380,13 +380,13 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         const double v = r.v;
         const int a = r.a;
         const unsigned ms = r.ms, mk = r.mk;
-        o.m_out = 0.0; o.mprev_out = 0.0; o.g_out = -1;
-        o.act_prev = false; o.jump = false; o.any_jump = false;
+        o.jump = false; o.any_jump = false;
         unsigned pend = __ballot_sync(FULL_MASK, r.active);
         bool mine = r.active;
         unsigned fm, fin;
         double m_prev;
-        auto round = [&]() {
+        auto round = [&](auto first_tag) {
+            constexpr bool FIRST = decltype(first_tag)::value;   // first round of the batch: every active row is pending
             const double c_ms0 = h.smax, c_ub = h.sub2;
             const int c_g = ga.sarg;
             const bool T = mine && upd && a == c_g;
@@ -420,10 +420,14 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             fin = fm ? (pend & ((fm & (0u - fm)) - 1u)) : pend;
             __syncwarp();
             const bool done = mine & ((fin & bit) != 0);
-            o.g_out = done ? c_g : o.g_out;
-            o.m_out = done ? m_k : o.m_out;
-            o.mprev_out = done ? m_prev : o.mprev_out;
-            o.act_prev = done ? (ga.actstep != -1) : o.act_prev;
+            if (FIRST) {   // rows that are not done yet are overwritten by a later round or by their replay
+                o.g_out = c_g; o.m_out = m_k; o.mprev_out = m_prev; o.act_prev = ga.actstep != -1;
+            } else {
+                o.g_out = done ? c_g : o.g_out;
+                o.m_out = done ? m_k : o.m_out;
+                o.mprev_out = done ? m_prev : o.mprev_out;
+                o.act_prev = done ? (ga.actstep != -1) : o.act_prev;
+            }
             if (done & upd & ((mk & fin & gt) == 0)) cell->val = v;
             const bool last_of_state = done & ((ms & fin & gt) == 0);
             if (last_of_state) sh->smax = m_k;
@@ -431,7 +435,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 if (last_of_state & ((lm & ms & fin) != 0)) sh->sub2 = runner_up_bound((lifter & (v > B)) ? v : B, m_k);
             }
         };
-        round();
+        round(std::true_type{});
         if (fm != 0) {
             for (;;) {
                 // ---- exact replay of the first doubtful row j
@@ -472,7 +476,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 if (pend == 0) break;
                 h = *sh;
                 ga = *sa;
-                round();
+                round(std::false_type{});
                 if (fm == 0) break;
             }
         }
