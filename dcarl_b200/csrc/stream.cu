@@ -168,6 +168,39 @@ __device__ __forceinline__ void warp_top2_small(const double *row, int stride, i
     second = key_to_double(H2, L2);
 }
 
+// One step of an inclusive warp scan: x += (value `off` lanes below), using the in-range predicate
+// the shuffle itself returns (no lane compare).
+__device__ __forceinline__ float scan_step(float x, int off) {
+    float r;
+    asm volatile(
+        "{\n"
+        ".reg .f32 t;\n"
+        ".reg .pred p;\n"
+        "shfl.sync.up.b32 t|p, %1, %2, 0, 0xffffffff;\n"
+        "mov.f32 %0, %1;\n"
+        "@p add.f32 %0, %1, t;\n"
+        "}\n"
+        : "=f"(r) : "f"(x), "r"(off));
+    return r;
+}
+__device__ __forceinline__ double scan_step(double x, int off) {
+    double r;
+    asm volatile(
+        "{\n"
+        ".reg .b32 lo, hi, tl, th;\n"
+        ".reg .f64 t;\n"
+        ".reg .pred p;\n"
+        "mov.b64 {lo, hi}, %1;\n"
+        "shfl.sync.up.b32 tl|p, lo, %2, 0, 0xffffffff;\n"
+        "shfl.sync.up.b32 th|p, hi, %2, 0, 0xffffffff;\n"
+        "mov.b64 t, {tl, th};\n"
+        "mov.f64 %0, %1;\n"
+        "@p add.f64 %0, %1, t;\n"
+        "}\n"
+        : "=d"(r) : "d"(x), "r"(off));
+    return r;
+}
+
 struct Cell {
     double s1, s2, val;
 };
@@ -280,7 +313,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     const unsigned ebase = (unsigned)inst * n_steps + lane;
 
     double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
-    unsigned max_idx = 0, max_act = 0;   // lane-local maxima of the raw keys: out-of-range rows show up here
+    unsigned clamped = 0;   // lane-local OR of (raw key ^ clamped key): non-zero once a row was out of range
 
     int n_idx = 0, n_act = 0;
     RT n_R = RT(0);
@@ -316,8 +349,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         // (lanes past the end of the stream re-read keys that were already checked)
         const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
         const int a = (int)min((unsigned)n_act, (unsigned)(A - 1));
-        max_idx = max(max_idx, (unsigned)n_idx);
-        max_act = max(max_act, (unsigned)n_act);
+        clamped |= (unsigned)(n_idx ^ s_in) | (unsigned)(n_act ^ a);
         m.rin = n_R;
         const unsigned e = ebase + (k - lane);
         if (k + 32 < n_steps) { n_idx = ld_stream(gidx + e + 32); n_act = ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
@@ -498,26 +530,17 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             if constexpr (SCAN_F32) {
                 float f = (float)d;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const float q = __shfl_up_sync(FULL_MASK, f, off);
-                    if (lane >= off) f += q;
-                }
+                for (int off = 1; off < 32; off <<= 1) f = scan_step(f, off);
                 pre = (double)f;
             } else {
                 pre = d;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const double q = __shfl_up_sync(FULL_MASK, pre, off);
-                    if (lane >= off) pre += q;
-                }
+                for (int off = 1; off < 32; off <<= 1) pre = scan_step(pre, off);
             }
             if (o.any_jump) {   // rare: a state activates at this row, its (max + bonus) enters the sum
                 double jmp = o.jump ? o.m_out + bonus : 0.0;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const double q = __shfl_up_sync(FULL_MASK, jmp, off);
-                    if (lane >= off) jmp += q;
-                }
+                for (int off = 1; off < 32; off <<= 1) jmp = scan_step(jmp, off);
                 pre += jmp;
             }
             const double ov = total + pre;
@@ -582,7 +605,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         for (int a = lane; a < A; a += 32)
             if (hist[a]) atomicAdd(p.act_hist + a, (unsigned long long)hist[a]);
     }
-    if (p.bad_rows != nullptr && (max_idx >= (unsigned)S || max_act >= (unsigned)A)) atomicAdd(p.bad_rows, 1ull);
+    if (p.bad_rows != nullptr && clamped) atomicAdd(p.bad_rows, 1ull);
 }
 
 // ---- general-shape walker: tables in global memory, one row at a time ----------------------
