@@ -20,7 +20,7 @@ from .sampling import (Data_Generation, add_an_act_data, generate, random_state_
 from .rls import RLS, BoxBuffer, VISITED_STATE_DIST  # noqa: F401
 from .rollout import rollout_cv  # noqa: F401
 from .frenet import (FrenetParams, FrenetResult, JunctionTrajectoryPlanner, Routes, TrajectoryAction,  # noqa: F401
-                     dense_polyline2d, frenet_params, frenet_plan, frenet_state)
+                     dense_polyline2d, frenet_params, frenet_plan, frenet_start)
 from .io import load_rls_buffer, load_sim_data, save_rls_buffer  # noqa: F401
 from . import dist  # noqa: F401
 

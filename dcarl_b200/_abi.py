@@ -86,6 +86,7 @@ SIGNATURES = {
     "dcarl_rollout_cv": (_int, [_vp, _vp, _i64, _i32, _f, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dcarl_default_frenet_params": (None, [C.POINTER(FrenetParams)]),
     "dcarl_spline_build": (_int, [_vp, _vp, _i32, _vp, _vp]),
+    "dcarl_frenet_start": (_int, [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     "dcarl_frenet_plan": (_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.POINTER(FrenetParams),
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -144,6 +144,92 @@ __device__ __forceinline__ int warp_argmin(double cost, int idx) {
     return idx;
 }
 
+// ---- calculate_start_state (JTP:248-276): the ego projected on its route ------------------------
+// tools.get_frenet_state (tools.py:235-270) over dist_from_point_to_polyline2d (tools.py:138-232) on
+// the route's knots (columns ax, ay of coef; column s is the arc length the reference re-sums), with
+// the all-zero tangent table the planner passes (JTP:84).  One warp per scenario: the lanes scan
+// the knots for the closest one (first minimum, like np.argmin), the case analysis on the one or
+// two adjacent segments is evaluated redundantly by every lane.
+// ego [n,5] = {x, y, vx, vy, v}  ->  start [n,5] = {s0, c_d = -d, c_d_d = vd, 0, c_speed = v}
+__device__ __forceinline__ void point_to_segment(double x0, double y0, double x1, double y1, double x2, double y2,
+                                                 double &dl, double &d1, double &d2) {   // tools.py:122-135
+    const double l = sqrt((y2 - y1) * (y2 - y1) + (x2 - x1) * (x2 - x1));
+    if (l == 0.0) { dl = sqrt((y0 - y1) * (y0 - y1) + (x0 - x1) * (x0 - x1)); d1 = 0.0; d2 = 0.0; return; }
+    dl = ((y2 - y1) * x0 - (x2 - x1) * y0 + x2 * y1 - x1 * y2) / l;
+    d1 = (x1 * x1 + x0 * (x2 - x1) - x1 * x2 + y1 * y1 + y0 * (y2 - y1) - y1 * y2) / l;
+    d2 = (x2 * x2 - x0 * (x2 - x1) - x1 * x2 + y2 * y2 - y0 * (y2 - y1) - y1 * y2) / l;
+}
+
+__global__ void __launch_bounds__(kFrWarpsPerCta * 32) k_frenet_start(const double *__restrict__ coef,
+                                                                      const long long *__restrict__ knot_off,
+                                                                      int n_paths, const int *__restrict__ path_id,
+                                                                      const double *__restrict__ ego, long long n,
+                                                                      double *__restrict__ start) {
+    const int lane = lane_id();
+    const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
+    const long long sc = (long long)blockIdx.x * kFrWarpsPerCta + warp;
+    if (sc >= n) return;
+    const int pid = path_id[sc];
+    const bool path_ok = pid >= 0 && pid < n_paths;
+    const long long k0 = path_ok ? knot_off[pid] : 0;
+    const int nk = path_ok ? (int)(knot_off[pid + 1] - k0) : 0;
+    double *o = start + 5 * sc;
+    if (nk < 2) {   // warp-uniform
+        if (lane < 5) o[lane] = CUDART_NAN;
+        return;
+    }
+    const double *c = coef + 9 * k0;
+    const double x0 = ego[5 * sc], y0 = ego[5 * sc + 1], vx = ego[5 * sc + 2], vy = ego[5 * sc + 3], v = ego[5 * sc + 4];
+    double best = CUDART_INF;
+    int bi = -1;
+    for (int i = lane; i < nk; i += 32) {
+        const double dx = c[9 * (size_t)i + 1] - x0, dy = c[9 * (size_t)i + 5] - y0;
+        const double d = sqrt(dx * dx + dy * dy);
+        if (d < best) { best = d; bi = i; }   // ascending i per lane: strict compare keeps the first
+    }
+    const int ci = warp_argmin(best, bi);
+    const double cdx = c[9 * (size_t)ci + 1] - x0, cdy = c[9 * (size_t)ci + 5] - y0;
+    const double dmin_ = sqrt(cdx * cdx + cdy * cdy);   // dist_line[closest_idx]
+    auto X = [&](int i) { return c[9 * (size_t)i + 1]; };
+    auto Y = [&](int i) { return c[9 * (size_t)i + 5]; };
+    auto S = [&](int i) { return c[9 * (size_t)i]; };
+    double dc = 0.0, nh = 0.0, nt = 0.0, ph = 0.0, pt = 0.0, dn = 0.0, dp = 0.0;
+    int ctype = 0;
+    if (ci == 0) {
+        point_to_segment(x0, y0, X(0), Y(0), X(1), Y(1), dn, nh, nt);
+        if (nh < 0) dc = dn < 0 ? -dmin_ : dmin_;
+        else { dc = dn; ctype = 1; }
+    } else if (ci == nk - 1) {
+        point_to_segment(x0, y0, X(nk - 2), Y(nk - 2), X(nk - 1), Y(nk - 1), dp, ph, pt);
+        if (pt < 0) dc = dp < 0 ? -dmin_ : dmin_;
+        else { dc = dp; ctype = -1; }
+    } else {
+        point_to_segment(x0, y0, X(ci - 1), Y(ci - 1), X(ci), Y(ci), dp, ph, pt);
+        point_to_segment(x0, y0, X(ci), Y(ci), X(ci + 1), Y(ci + 1), dn, nh, nt);
+        if (pt < 0 && nh < 0) {
+            double sg, u1, u2;
+            point_to_segment(X(ci + 1), Y(ci + 1), X(ci - 1), Y(ci - 1), X(ci), Y(ci), sg, u1, u2);
+            dc = sg > 0 ? -dmin_ : dmin_;
+        } else if (pt < 0) { dc = dn; ctype = 1; }
+        else if (nh < 0) { dc = dp; ctype = -1; }
+        else if (fabs(dn) > fabs(dp)) { dc = dp; ctype = -1; }
+        else { dc = dn; ctype = 1; }
+    }
+    double s, psi;
+    if (ctype == 1) { s = nh + S(ci); psi = atan2(Y(ci + 1) - Y(ci), X(ci + 1) - X(ci)); }
+    else if (ctype == -1) { s = ph + S(ci - 1); psi = atan2(Y(ci) - Y(ci - 1), X(ci) - X(ci - 1)); }
+    else { s = S(ci); psi = 0.0; }                                             // tangents[nearest_idx] == 0 (JTP:84)
+    double sn, cs;
+    sincos(psi, &sn, &cs);
+    if (lane == 0) {
+        o[0] = s;
+        o[1] = -dc;                   // JTP:269
+        o[2] = -sn * vx + cs * vy;    // tools.py:262-268
+        o[3] = 0.0;
+        o[4] = v;                     // JTP:263
+    }
+}
+
 struct FrenetArgs {
     const double *coef;
     const long long *knot_off;
@@ -404,6 +490,21 @@ extern "C" int dcarl_spline_build(const double *knots_xy, const int64_t *knot_of
     k_spline_build<<<(unsigned)((n_paths + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         knots_xy, reinterpret_cast<const long long *>(knot_off), n_paths, coef);
     DCARL_LAUNCH_CHECK("k_spline_build");
+    return 0;
+}
+
+extern "C" int dcarl_frenet_start(const double *coef, const int64_t *knot_off, int32_t n_paths, const int32_t *path_id,
+                                  const double *ego, int64_t n, double *out_start, dcarl_stream_t stream) {
+    if (n < 0) return bad_arg(6, "n < 0");
+    if (n == 0) return 0;
+    if (n_paths < 1 || !coef || !knot_off) return bad_arg(1, "no routes");
+    if (!path_id || !ego) return bad_arg(4, "null scenario input");
+    if (!out_start) return bad_arg(7, "out_start is null");
+    if ((n + kFrWarpsPerCta - 1) / kFrWarpsPerCta > 0x7fffffffll) return bad_arg(6, "n too large for one launch");
+    const long long grid = (n + kFrWarpsPerCta - 1) / kFrWarpsPerCta;
+    k_frenet_start<<<(unsigned)grid, kFrWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
+        coef, reinterpret_cast<const long long *>(knot_off), n_paths, path_id, ego, n, out_start);
+    DCARL_LAUNCH_CHECK("k_frenet_start");
     return 0;
 }
 

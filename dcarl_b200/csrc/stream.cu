@@ -481,6 +481,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 double mx, second; int arg;
                 if (A <= 32) warp_top2_small(&cells[sj * A].val, 3, A, mx, arg, second);
                 else warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
+                __syncwarp();   // every lane has read the state record and the values before lane j rewrites them
                 // The argmax only ever changes here, so a state can only activate here (ST1:98-99):
                 // between two exact rows "argmax != rule" implies "already activated".
                 const bool activates = oa.actstep == -1 && arg != rule;

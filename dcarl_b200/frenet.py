@@ -6,13 +6,13 @@ cubic_spline_planner.py (SPL) and the two helpers of tools.py it needs:
 
     frenet_params(**constants)            the module constants JTP:13-39 -> the planner's sample grids
     Routes(polylines)                     build_frenet_path / generate_target_course (JTP:79-90, 279-290)
+    frenet_start(routes, path_id, ego)                           calculate_start_state (JTP:248-276) for n scenarios
     frenet_plan(routes, path_id, start, ego_xy, obs, n_obs)      one planning tick for n scenarios
     JunctionTrajectoryPlanner             drop-in class: trajectory_update(dynamic_map) -> (TrajectoryAction, index)
 
 The batched call is the product path: one warp per scenario (csrc/frenet.cu).  numpy in -> numpy out,
 CUDA tensors in -> CUDA tensors out.  No CPU fallback: without the built library or a device it raises.
 """
-import math
 from dataclasses import dataclass
 from typing import Optional
 
@@ -147,69 +147,20 @@ class TrajectoryAction(object):
         self.desired_speed = desired_speed
 
 
-def _point_to_segment(x0, y0, x1, y1, x2, y2):
-    """tools.py:122-135 dist_from_point_to_line2d."""
-    l = math.sqrt((y2 - y1) * (y2 - y1) + (x2 - x1) * (x2 - x1))
-    if l == 0:
-        return math.sqrt((y0 - y1) * (y0 - y1) + (x0 - x1) * (x0 - x1)), 0, 0
-    dl = ((y2 - y1) * x0 - (x2 - x1) * y0 + x2 * y1 - x1 * y2) / l
-    d1 = (x1 * x1 + x0 * (x2 - x1) - x1 * x2 + y1 * y1 + y0 * (y2 - y1) - y1 * y2) / l
-    d2 = (x2 * x2 - x0 * (x2 - x1) - x1 * x2 + y2 * y2 - y0 * (y2 - y1) - y1 * y2) / l
-    return dl, d1, d2
-
-
-def frenet_state(x0, y0, vx, vy, line):
-    """Caller-side geometry of calculate_start_state (JTP:248-276): tools.get_frenet_state (tools.py:235-270)
-    over dist_from_point_to_polyline2d (tools.py:138-232), with the all-zero tangent table the planner passes
-    (JTP:84).  Returns (s, d, vd): arc length of the foot point, signed lateral distance, lateral speed.
-    Host scalar code: the per-tick ego projection the reference's caller performs before planning."""
-    line = np.asarray(line, np.float64)
-    dist_line = np.linalg.norm(line - [x0, y0], axis=1)
-    ci = int(np.argmin(dist_line))
-    n = len(line)
-    ctype = 0
-    seg = lambda i, j: _point_to_segment(x0, y0, line[i, 0], line[i, 1], line[j, 0], line[j, 1])
-    nh = nt = ph = pt = 0.0
-    if ci == 0:
-        dn, nh, nt = seg(0, 1)
-        if nh < 0:
-            dc = dist_line[ci] * (-1 if dn < 0 else 1)
-        else:
-            dc, ctype = dn, 1
-    elif ci == n - 1:
-        dp, ph, pt = seg(n - 2, n - 1)
-        if pt < 0:
-            dc = dist_line[ci] * (-1 if dp < 0 else 1)
-        else:
-            dc, ctype = dp, -1
-    else:
-        dp, ph, pt = seg(ci - 1, ci)
-        dn, nh, nt = seg(ci, ci + 1)
-        if pt < 0 and nh < 0:
-            dc = dist_line[ci]
-            if _point_to_segment(line[ci + 1, 0], line[ci + 1, 1], line[ci - 1, 0], line[ci - 1, 1],
-                                 line[ci, 0], line[ci, 1])[0] > 0:
-                dc *= -1
-        elif pt < 0:
-            dc, ctype = dn, 1
-        elif nh < 0:
-            dc, ctype = dp, -1
-        elif abs(dn) > abs(dp):
-            dc, ctype = dp, -1
-        else:
-            dc, ctype = dn, 1
-    seglen = lambda pts: np.sum(np.linalg.norm(np.diff(pts, axis=0), axis=1))
-    if ctype == 1:
-        s = nh + seglen(line[:ci + 1])
-        psi = math.atan2(line[ci + 1, 1] - line[ci, 1], line[ci + 1, 0] - line[ci, 0])
-    elif ctype == -1:
-        s = ph + seglen(line[:ci])
-        psi = math.atan2(line[ci, 1] - line[ci - 1, 1], line[ci, 0] - line[ci - 1, 0])
-    else:
-        s = seglen(line[:ci + 1])
-        psi = 0.0
-    vd = -math.sin(psi) * vx + math.cos(psi) * vy
-    return float(s), float(dc), float(vd)
+def frenet_start(routes, path_id, ego, *, stream=None):
+    """calculate_start_state (JTP:248-276) for n scenarios: ego [n, 5] = {x, y, vx, vy, v} projected on
+    route path_id[i] (tools.get_frenet_state, tools.py:138-270) -> start [n, 5] = {s0, c_d, c_d_d, 0, c_speed},
+    the `start` input of frenet_plan.  numpy in -> numpy out, CUDA tensors in -> CUDA tensor out."""
+    _dev.require_cuda()
+    on_device = _dev.is_device(ego)
+    dv = routes.device
+    d_pid = _dev.as_device(path_id, torch.int32, dv).reshape(-1)
+    n = int(d_pid.shape[0])
+    d_ego = _dev.as_device(ego, torch.float64, dv).reshape(n, 5)
+    out = torch.empty((n, 5), dtype=torch.float64, device=dv)
+    _abi.check(_abi.lib().dcarl_frenet_start(_dev.ptr(routes.coef), _dev.ptr(routes.knot_off), routes.n_paths,
+                                             _dev.ptr(d_pid), _dev.ptr(d_ego), n, _dev.ptr(out), _dev.stream_handle(stream)))
+    return out if on_device else out.cpu().numpy()
 
 
 class JunctionTrajectoryPlanner(object):
@@ -240,8 +191,7 @@ class JunctionTrajectoryPlanner(object):
         if self.routes is None or getattr(dynamic_map, "lanes_updated", False):
             self.build_frenet_path(dynamic_map, True)
         ego = dynamic_map.ego_vehicle
-        s0, d, vd = frenet_state(ego.x, ego.y, ego.vx, ego.vy, self.ref_path)
-        start = np.array([[s0, -d, vd, 0.0, ego.v]])                           # JTP:268-273
+        start = frenet_start(self.routes, [0], [[ego.x, ego.y, ego.vx, ego.vy, ego.v]])   # JTP:248-276
         veh = list(dynamic_map.vehicles)
         obs = np.array([[v.x, v.y, v.vx, v.vy, v.yaw] for v in veh], np.float64).reshape(1, -1, 5)
         if obs.shape[1] > 32:                                                   # the kernel ranks at most 32

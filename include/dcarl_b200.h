@@ -229,6 +229,12 @@ typedef struct dcarl_frenet_params {
 void dcarl_default_frenet_params(dcarl_frenet_params *p);   /* host pointer; the shipped constants */
 int dcarl_spline_build(const double *knots_xy, const int64_t *knot_off, int32_t n_paths, double *coef,
                        dcarl_stream_t stream);
+/* calculate_start_state (JTP:248-276): ego [n, 5] = {x, y, vx, vy, v} projected on route path_id[i]
+ * (tools.get_frenet_state, tools.py:138-270, on the route's knots with the zero tangent table of
+ * JTP:84) -> out_start [n, 5] = {s0, c_d, c_d_d, 0, c_speed}, the `start` input of dcarl_frenet_plan.
+ * NaN for a path_id outside the routes. */
+int dcarl_frenet_start(const double *coef, const int64_t *knot_off, int32_t n_paths, const int32_t *path_id,
+                       const double *ego, int64_t n, double *out_start, dcarl_stream_t stream);
 int dcarl_frenet_plan(const double *coef, const int64_t *knot_off, int32_t n_paths, const int32_t *path_id,
                       const double *start, const double *ego_xy, const double *obs, const int32_t *n_obs,
                       int32_t max_obs, int64_t n, const dcarl_frenet_params *p /* host */,

@@ -1,5 +1,7 @@
 """Shared helpers of the Frenet-planner tests: golden fixture -> batched planner inputs, and a
 synthetic scenario generator for sizes the golden file does not cover."""
+import math
+
 import numpy as np
 
 
@@ -68,3 +70,70 @@ def synth_scenarios(rng, n, knots, knot_off, max_obs=6):
             v, yaw = rng.uniform(0, 2.0), rng.uniform(-3.14, 3.14)
             obs[i, q] = [pos[0], pos[1], v * np.cos(yaw), v * np.sin(yaw), yaw]
     return path_id, start, ego, obs, n_obs
+
+
+def _point_to_segment(x0, y0, x1, y1, x2, y2):
+    """tools.py:122-135 dist_from_point_to_line2d."""
+    l = math.sqrt((y2 - y1) * (y2 - y1) + (x2 - x1) * (x2 - x1))
+    if l == 0:
+        return math.sqrt((y0 - y1) * (y0 - y1) + (x0 - x1) * (x0 - x1)), 0, 0
+    dl = ((y2 - y1) * x0 - (x2 - x1) * y0 + x2 * y1 - x1 * y2) / l
+    d1 = (x1 * x1 + x0 * (x2 - x1) - x1 * x2 + y1 * y1 + y0 * (y2 - y1) - y1 * y2) / l
+    d2 = (x2 * x2 - x0 * (x2 - x1) - x1 * x2 + y2 * y2 - y0 * (y2 - y1) - y1 * y2) / l
+    return dl, d1, d2
+
+
+def frenet_state(x0, y0, vx, vy, line):
+    """numpy restatement (test infrastructure) of calculate_start_state (JTP:248-276): tools.get_frenet_state
+    (tools.py:235-270) over dist_from_point_to_polyline2d (tools.py:138-232), with the all-zero tangent table
+    the planner passes (JTP:84).  Returns (s, d, vd).  Pinned against the reference's run in test_frenet_cpu.py;
+    the product computes this on the device (dcarl_frenet_start)."""
+    line = np.asarray(line, np.float64)
+    dist_line = np.linalg.norm(line - [x0, y0], axis=1)
+    ci = int(np.argmin(dist_line))
+    n = len(line)
+    ctype = 0
+    seg = lambda i, j: _point_to_segment(x0, y0, line[i, 0], line[i, 1], line[j, 0], line[j, 1])
+    nh = nt = ph = pt = 0.0
+    if ci == 0:
+        dn, nh, nt = seg(0, 1)
+        if nh < 0:
+            dc = dist_line[ci] * (-1 if dn < 0 else 1)
+        else:
+            dc, ctype = dn, 1
+    elif ci == n - 1:
+        dp, ph, pt = seg(n - 2, n - 1)
+        if pt < 0:
+            dc = dist_line[ci] * (-1 if dp < 0 else 1)
+        else:
+            dc, ctype = dp, -1
+    else:
+        dp, ph, pt = seg(ci - 1, ci)
+        dn, nh, nt = seg(ci, ci + 1)
+        if pt < 0 and nh < 0:
+            dc = dist_line[ci]
+            if _point_to_segment(line[ci + 1, 0], line[ci + 1, 1], line[ci - 1, 0], line[ci - 1, 1],
+                                 line[ci, 0], line[ci, 1])[0] > 0:
+                dc *= -1
+        elif pt < 0:
+            dc, ctype = dn, 1
+        elif nh < 0:
+            dc, ctype = dp, -1
+        elif abs(dn) > abs(dp):
+            dc, ctype = dp, -1
+        else:
+            dc, ctype = dn, 1
+    seglen = lambda pts: np.sum(np.linalg.norm(np.diff(pts, axis=0), axis=1))
+    if ctype == 1:
+        s = nh + seglen(line[:ci + 1])
+        psi = math.atan2(line[ci + 1, 1] - line[ci, 1], line[ci + 1, 0] - line[ci, 0])
+    elif ctype == -1:
+        s = ph + seglen(line[:ci])
+        psi = math.atan2(line[ci, 1] - line[ci - 1, 1], line[ci, 0] - line[ci - 1, 0])
+    else:
+        s = seglen(line[:ci + 1])
+        psi = 0.0
+    vd = -math.sin(psi) * vx + math.cos(psi) * vy
+    return float(s), float(dc), float(vd)
+
+

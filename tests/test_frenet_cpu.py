@@ -1,11 +1,11 @@
-"""Host-side logic of dcarl_b200.frenet that needs no device: the sample grids, the route ingest and
-the caller-side Frenet projection, against the reference's golden run."""
+"""Host-side logic of dcarl_b200.frenet that needs no device (the sample grids, the route ingest) and the
+test-side numpy restatement of the ego projection, against the reference's golden run."""
 import numpy as np
 import pytest
 
 from dcarl_b200 import frenet as fr
 from oracle import cport
-from helpers_frenet import params_from_golden
+from helpers_frenet import frenet_state, params_from_golden
 
 
 @pytest.fixture(scope="module")
@@ -29,5 +29,5 @@ def test_route_ingest_and_start_state_match_the_reference(g):
         dense = fr.dense_polyline2d(g["lane_xy"][i, :nl], 2)
         assert dense.shape == (nk, 2)
         assert np.array_equal(dense[:, 0], g["knots_x"][i, :nk]) and np.array_equal(dense[:, 1], g["knots_y"][i, :nk])
-        s, d, vd = fr.frenet_state(g["ego_xy"][i, 0], g["ego_xy"][i, 1], g["ego_v"][i, 0], g["ego_v"][i, 1], dense)
+        s, d, vd = frenet_state(g["ego_xy"][i, 0], g["ego_xy"][i, 1], g["ego_v"][i, 0], g["ego_v"][i, 1], dense)
         assert np.allclose([s, -d, vd], g["start"][i, :3], rtol=0, atol=1e-12)

@@ -10,7 +10,7 @@ import torch
 import dcarl_b200 as dc
 from dcarl_b200 import frenet as fr
 from oracle import cport
-from helpers_frenet import golden_batch, params_from_golden, synth_routes, synth_scenarios
+from helpers_frenet import frenet_state, golden_batch, params_from_golden, synth_routes, synth_scenarios
 
 pytestmark = pytest.mark.gpu
 
@@ -118,6 +118,27 @@ def test_device_tensors_no_obstacles_and_bad_route_id():
     assert empty.index.shape == (0,)
     with pytest.raises(dc.DcarlError):
         fr.frenet_plan(routes, pid, start, ego, obs, n_obs, fr.frenet_params(D_ROAD_W=1, MAX_LEFT_WIDTH=-7, MAX_RIGHT_WIDTH=7, N_S_SAMPLE=2))   # 60 candidates
+
+
+def test_start_state_matches_the_reference_and_the_numpy_restatement(g):
+    b = golden_batch(g)
+    routes = _routes_from(b)
+    ego = np.concatenate([g["ego_xy"], g["ego_v"]], axis=1)                 # x, y, vx, vy, v
+    start = fr.frenet_start(routes, b["path_id"], ego)
+    assert np.abs(start - g["start"]).max() < 1e-9                          # calculate_start_state of the reference run
+    # random egos around random routes, incl. beyond both ends of the route
+    rng = np.random.default_rng(21)
+    knots, off = synth_routes(rng, 12)
+    routes = fr.Routes([knots[off[i]:off[i + 1]] for i in range(12)])
+    n = 4000
+    pid = rng.integers(0, 12, n).astype(np.int32)
+    j = off[:-1][pid] + (rng.random(n) * (off[1:] - off[:-1])[pid]).astype(np.int64)
+    ego = np.concatenate([knots[j] + rng.normal(0, 6, (n, 2)), rng.normal(0, 5, (n, 2)), rng.uniform(0, 15, (n, 1))], axis=1)
+    got = fr.frenet_start(routes, pid, ego)
+    for i in range(n):
+        s, d, vd = frenet_state(ego[i, 0], ego[i, 1], ego[i, 2], ego[i, 3], knots[off[pid[i]]:off[pid[i] + 1]])
+        assert np.allclose(got[i], [s, -d, vd, 0.0, ego[i, 4]], rtol=0, atol=1e-9), i
+    assert np.isnan(fr.frenet_start(routes, [12], ego[:1])).all()          # route id out of range
 
 
 def test_drop_in_planner_class_reproduces_the_reference_tick(g):

@@ -16,7 +16,8 @@ import dcarl_b200 as dc  # noqa: E402
 from helpers import compare_stream, synth_streams  # noqa: E402
 from oracle import cport  # noqa: E402
 
-for (n_inst, n_steps, S, A, kw) in [(9, 700, 20, 11, {}), (5, 333, 1, 30, {}), (3, 200, 3, 40, {}), (4, 300, 40, 5, {"rule_act": 3})]:
+for (n_inst, n_steps, S, A, kw) in [(9, 700, 20, 11, {}), (5, 333, 1, 30, {}), (3, 200, 3, 40, {}), (4, 300, 40, 5, {"rule_act": 3}),
+                                    (4, 300, 4, 6, {"rule_act": 3, "prior_other": 100.0})]:
     idx, act, R = synth_streams(n_inst, n_steps, S, A, seed=n_steps, r_dtype=np.float64)
     ref = cport.stream(idx, act, R, S, A, cport.default_params(**kw))
     for variant in (0, 1):
@@ -46,5 +47,15 @@ dc.sample_returns(rng.uniform(-50, 100, (20, 11)), z, rng.integers(0, 11, 5000),
 dc.sample_returns_philox(torch.rand((20, 11), device="cuda"), 5000, 3)
 s0 = rng.uniform(-5, 5, (1000, 20)).astype(np.float32)
 dc.rollout_cv(s0, rng.integers(0, 11, 1000))
+# Frenet planner: spline build + one planning tick, against the oracle
+from helpers_frenet import synth_routes, synth_scenarios  # noqa: E402
+knots, off = synth_routes(rng, 4)
+pid, start, ego, obs, n_obs = synth_scenarios(rng, 300, knots, off, max_obs=5)
+routes = dc.Routes([knots[off[i]:off[i + 1]] for i in range(4)])
+res = dc.frenet_plan(routes, pid, start, ego, obs, n_obs, want_paths=True)
+coef = np.concatenate([cport.spline_build(knots[off[i]:off[i + 1]]) for i in range(4)])
+ref = cport.frenet_plan(coef, off, pid, start, ego, obs, n_obs, cport.frenet_params())
+assert np.array_equal(res.index, ref["index"])
+print("frenet ok")
 torch.cuda.synchronize()
 print("all kernels ran")
