@@ -106,12 +106,22 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
     float *shi = slo + p.Q * D;
     size_t off = kStages * (tile_bytes + ret_bytes) + (size_t)2 * p.Q * D * sizeof(float);
     off = (off + 15) & ~(size_t)15;
+    // head thresholds {lo0, hi0, lo1, hi1 | lo2, hi2, lo3, hi3} per query: two 16-byte broadcast loads
+    // per (warp, query) instead of eight 4-byte ones (with many queries the scan is bound by them)
+    float4 *shead = reinterpret_cast<float4 *>(smem_raw + off);
+    off += (size_t)p.Q * 2 * sizeof(float4);
     double *sbins = reinterpret_cast<double *>(smem_raw + off);
     const int nbins = p.Q * p.n_actions;
     off += p.bins_in_smem ? (size_t)nbins * 3 * sizeof(double) : 0;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + off);
 
     for (int i = tid; i < p.Q * D; i += kTileRows) { slo[i] = p.lo[i]; shi[i] = p.hi[i]; }
+    if (DT >= 4)
+        for (int q = tid; q < p.Q; q += kTileRows) {
+            const float *l = p.lo + (size_t)q * D, *h = p.hi + (size_t)q * D;
+            shead[2 * q] = make_float4(l[0], h[0], l[1], h[1]);
+            shead[2 * q + 1] = make_float4(l[2], h[2], l[3], h[3]);
+        }
     if (p.bins_in_smem)
         for (int i = tid; i < nbins * 3; i += kTileRows) sbins[i] = 0.0;
     if (tid == 0) {
@@ -166,8 +176,14 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
             bool ok = in_buf;
             if (DT > 0) {
                 constexpr int kHead = DT < 4 ? DT : 4;
+                if (DT >= 4) {
+                    const float4 t0 = shead[2 * q], t1 = shead[2 * q + 1];
+                    ok = ok & (xr[0] >= t0.x) & (xr[0] <= t0.y) & (xr[1] >= t0.z) & (xr[1] <= t0.w) &
+                         (xr[2] >= t1.x) & (xr[2] <= t1.y) & (xr[3] >= t1.z) & (xr[3] <= t1.w);
+                } else {
 #pragma unroll
-                for (int d = 0; d < kHead; ++d) ok = ok && (xr[d] >= l[d]) && (xr[d] <= h[d]);
+                    for (int d = 0; d < kHead; ++d) ok = ok && (xr[d] >= l[d]) && (xr[d] <= h[d]);
+                }
                 // with many queries most (row, query) pairs die on the first dims: leave before the rest
                 if (p.Q > 1 && !__any_sync(FULL_MASK, ok)) continue;
 #pragma unroll
@@ -242,6 +258,7 @@ static size_t box_smem_bytes(int Q, int D, int n_actions, bool bins_in_smem) {
     const int W = D + 1;
     size_t off = (size_t)kStages * kTileRows * (W + 1) * sizeof(float) + (size_t)2 * Q * D * sizeof(float);
     off = (off + 15) & ~(size_t)15;
+    off += (size_t)Q * 32;   // head thresholds
     if (bins_in_smem) off += (size_t)Q * n_actions * 3 * sizeof(double);
     off += kStages * sizeof(uint64_t);
     return off;

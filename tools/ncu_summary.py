@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read on the CPU box): headline metrics + instructions per CUDA source line.
-usage: python tools/ncu_summary.py gpurun_out/stream_rows.ncu-rep [units_per_launch] [min_instr_per_unit]"""
+usage: python tools/ncu_summary.py gpurun_out/stream_rows.ncu-rep [units_per_launch] [min_instr_per_unit] [summary.json]
+With a fourth argument the DRAM traffic of the launch is also written as JSON (bench.py reads
+profiles/stream_rows_ncu_summary.json for roofline.traffic)."""
 import csv
 import io
 import subprocess
@@ -25,6 +27,18 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic"]
 print("kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
+if len(sys.argv) > 4:
+    import json
+    g = lambda name: float(vals[hdr.index(name)].replace(",", ""))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd = g("dram__bytes_read.sum") * scale[unit[hdr.index("dram__bytes_read.sum")]]
+    wr = g("dram__bytes_write.sum") * scale[unit[hdr.index("dram__bytes_write.sum")]]
+    tu = {"ns": 1e-3, "us": 1.0, "ms": 1e3}[unit[hdr.index("gpu__time_duration.sum")]]
+    json.dump({"kernel": vals[hdr.index("Kernel Name")], "source": f"ncu --set full, one launch ({rep})",
+               "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+               "inst_executed": g("smsp__inst_executed.sum"),
+               "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "gpu_time_us_under_ncu": g("gpu__time_duration.sum") * tu}, open(sys.argv[4], "w"), indent=1)
 for w in want:
     if w in hdr:
         i = hdr.index(w)
