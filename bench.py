@@ -53,7 +53,8 @@ def synth_host(n_inst, n_steps, seed):
     return idx.astype(np.int32), act.astype(np.int32), R
 
 
-def synth_device(n_inst, n_steps, seed, device):
+def synth_device(n_inst, n_steps, seed, device, S=S, A=A, live=None):
+    """Sim-2-shaped rows by default; S=1, A=30, live=11 gives the Simulation_1 shape (11 live actions)."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     q = torch.rand((n_inst, S * A), generator=g, device=device) * 150 - 50
@@ -69,7 +70,7 @@ def synth_device(n_inst, n_steps, seed, device):
             z[bad] = torch.randn(int(bad.sum()), generator=g, device=device)
             bad = (z < -3) | (z >= 3)
         i = torch.floor((3 + z) / 6 * S).clamp_(0, S - 1).long()
-        a = torch.randint(0, A, (hi - lo, n_steps), generator=g, device=device)
+        a = torch.randint(0, live or A, (hi - lo, n_steps), generator=g, device=device)
         R[lo:hi] = q[lo:hi].gather(1, i * A + a) + 50 * torch.randn((hi - lo, n_steps), generator=g, device=device)
         idx[lo:hi] = i.to(torch.int32)
         act[lo:hi] = a.to(torch.int32)

@@ -70,6 +70,7 @@ SIGNATURES = {
     "dcarl_default_rls_params": (None, [C.POINTER(RlsParams)]),
     "dcarl_bounds": (_int, [_vp, _int, _vp, _i64, C.POINTER(Params), _vp, _vp]),
     "dcarl_stream_bounds_ws": (_sz, [_i64, _i64, _i32, _i32]),
+    "dcarl_stream_rows_fit": (_int, [_i32, _i32]),
     "dcarl_stream_bounds": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i32, _i32, C.POINTER(Params),
                                    _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
     "dcarl_cell_values": (_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Params), _vp, _vp]),

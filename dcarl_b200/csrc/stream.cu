@@ -857,6 +857,11 @@ extern "C" size_t dcarl_stream_bounds_ws(int64_t n_inst, int64_t n_steps, int32_
     return (size_t)n_inst * walk_inst_bytes(S, A);
 }
 
+extern "C" int dcarl_stream_rows_fit(int32_t S, int32_t A) {
+    if (S <= 0 || A <= 0 || (long long)S * A > (1ll << 28)) return 0;
+    return kRowsCtaFixedBytes + rows_warp_bytes(S, A) <= kMaxSmemPerCta ? 1 : 0;
+}
+
 extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const void *R, int r_is_f64,
                                    int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
                                    const dcarl_params *p, void *out_value, int out_is_f64,

@@ -49,7 +49,8 @@ class StreamPlan:
         self.bad_rows = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.stats = e((STATS_HEADER + self.A,), torch.float64) if want_stats else None
         L = _abi.lib()
-        need = L.dcarl_stream_bounds_ws(self.n_inst, self.n_steps, self.S, self.A) if self.variant == 1 else 0
+        walker = self.variant == 1 or (self.variant == 0 and not L.dcarl_stream_rows_fit(self.S, self.A))
+        need = L.dcarl_stream_bounds_ws(self.n_inst, self.n_steps, self.S, self.A) if walker else 0
         self.ws = e((max(need, 16),), torch.uint8)
         self._ws_bytes = need
         self._pinned = None

@@ -89,10 +89,12 @@ int dcarl_bounds(const void *x, int x_is_f64, const int64_t *seg_offsets, int64_
  * index out of bounds, leave the outputs of their instance unspecified, and make *bad_rows
  * (nullable, uint64, accumulated) non-zero; callers must treat *bad_rows != 0 as a failed call.
  * variant: 0 = default (row-parallel shared-memory kernel when the S*A table fits in shared
- * memory, else the global-memory walker), 1 = force the walker (needs ws), 2 = force the
- * row-parallel kernel (error if it does not fit).
+ * memory, else the global-memory walker), 1 = force the walker, 2 = force the row-parallel kernel
+ * (error if it does not fit).  The walker needs a workspace of dcarl_stream_bounds_ws() bytes;
+ * dcarl_stream_rows_fit() tells whether variant 0 will use the row-parallel kernel (1) or the walker (0).
  */
 size_t dcarl_stream_bounds_ws(int64_t n_inst, int64_t n_steps, int32_t S, int32_t A);
+int dcarl_stream_rows_fit(int32_t S, int32_t A);
 int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const void *R, int r_is_f64,
                         int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
                         const dcarl_params *p /* host */,

@@ -75,6 +75,17 @@ def test_random_instances_vs_oracle_f64(shape, variant):
     compare_stream(res, _oracle(idx, act, R, S, A, **kw), value_tol=1e-9)
 
 
+def test_table_larger_than_shared_memory_takes_the_walker():
+    """40 states x 256 actions = 10 240 cells do not fit one CTA's shared memory: the default variant
+    must switch to the global-memory walker by itself (and variant 2 must refuse)."""
+    idx, act, R = synth_streams(2, 1500, 40, 256, seed=77, r_dtype=np.float64)
+    assert not _abi.lib().dcarl_stream_rows_fit(40, 256) and _abi.lib().dcarl_stream_rows_fit(30, 256)
+    res = dc.stream_bounds(idx, act, R, 40, 256)
+    compare_stream(res, _oracle(idx, act, R, 40, 256), value_tol=1e-9)
+    with pytest.raises(dc.DcarlError):
+        dc.stream_bounds(idx, act, R, 40, 256, variant=2)
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_float32_inputs_and_outputs(variant):
     idx, act, R = synth_streams(40, 3000, 20, 11, seed=99, r_dtype=np.float32)

@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n-inst", type=int, default=4096)
     ap.add_argument("--n-steps", type=int, default=20000)
+    ap.add_argument("--S", type=int, default=None)
+    ap.add_argument("--A", type=int, default=None)
+    ap.add_argument("--live", type=int, default=None, help="actions that occur in the rows (Simulation_1: 11 of 30)")
     ap.add_argument("--once", action="store_true")
     ap.add_argument("--no-overall", action="store_true")
     args = ap.parse_args()
@@ -35,8 +38,8 @@ def main():
 
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
-    idx, act, R = bench.synth_device(args.n_inst, args.n_steps, 1234, dev)
-    S, A = bench.S, bench.A
+    S, A = args.S or bench.S, args.A or bench.A
+    idx, act, R = bench.synth_device(args.n_inst, args.n_steps, 1234, dev, S=S, A=A, live=args.live)
     rows = args.n_inst * args.n_steps
     bps = 20 if args.no_overall else 24
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -44,7 +47,7 @@ def main():
     for v in [int(x) for x in args.variants.split(",")]:
         plan = dc.StreamPlan(args.n_inst, args.n_steps, S, A, want_overall=not args.no_overall,
                              want_stats=False, variant=v, device=dev)
-        out = {"variant": v, "n_inst": args.n_inst, "n_steps": args.n_steps}
+        out = {"variant": v, "n_inst": args.n_inst, "n_steps": args.n_steps, "S": S, "A": A}
         try:
             if args.once:
                 plan.run_device(idx, act, R)
