@@ -521,25 +521,28 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         if (OVERALL) {
             // rows of states that were active before the row: the bonus cancels in after - before
             const double d = (r.active && o.act_prev) ? o.m_out - o.mprev_out : 0.0;
-            double pre;
+            double pre, batch_sum;   // inclusive prefix of the deltas at this row, and over the whole batch
             if constexpr (SCAN_F32) {
                 float f = (float)d;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) f = scan_step(f, off);
                 pre = (double)f;
+                batch_sum = (double)__shfl_sync(FULL_MASK, f, 31);
             } else {
                 pre = d;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) pre = scan_step(pre, off);
+                batch_sum = shfl_f64(pre, 31);
             }
             if (o.any_jump) {   // rare: a state activates at this row, its (max + bonus) enters the sum
                 double jmp = o.jump ? o.m_out + bonus : 0.0;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) jmp = scan_step(jmp, off);
                 pre += jmp;
+                batch_sum += shfl_f64(jmp, 31);
             }
             const double ov = total + pre;
-            total += shfl_f64(pre, 31);
+            total += batch_sum;
             if (in_stream) st_stream(oall + e, (OT)ov);
         }
     };
