@@ -298,8 +298,11 @@ __global__ void __launch_bounds__(kFrWarpsPerCta * 32) k_frenet_plan(const Frene
     const int no = min(min(a.n_obs[sc], a.max_obs), 32);
     const int nuse = min(no, p.obstacles_considered);
     {
-        const double *o = a.obs + ((size_t)sc * a.max_obs + (lane < no ? lane : 0)) * 5;
-        const double ox = o[0], oy = o[1], ovx = o[2], ovy = o[3], oyaw = o[4];
+        double ox = 0.0, oy = 0.0, ovx = 0.0, ovy = 0.0, oyaw = 0.0;
+        if (lane < no) {   // obs may be null when max_obs == 0
+            const double *o = a.obs + ((size_t)sc * a.max_obs + lane) * 5;
+            ox = o[0]; oy = o[1]; ovx = o[2]; ovy = o[3]; oyaw = o[4];
+        }
         const double dx = ox - a.ego_xy[2 * sc], dy = oy - a.ego_xy[2 * sc + 1];
         const double dist = lane < no ? sqrt(dx * dx + dy * dy) : CUDART_INF;
         int rank = 0;

@@ -110,6 +110,8 @@ def test_device_tensors_no_obstacles_and_bad_route_id():
     assert res.index.is_cuda and bool(res.collision_free.all())             # no obstacles: nothing collides (PRD:23-24)
     host = fr.frenet_plan(routes, pid, start, ego, obs, np.zeros_like(n_obs))
     assert np.array_equal(host.index, res.index.cpu().numpy())
+    none = fr.frenet_plan(routes, pid, start, ego, np.zeros((64, 0, 5)), np.zeros(64, np.int32))   # no obstacle array at all
+    assert np.array_equal(none.index, host.index) and none.collision_free.all()
     bad = pid.copy()
     bad[7] = 3
     with pytest.raises(IndexError):
