@@ -59,6 +59,25 @@ def test_plan_matches_the_reference_run(g):
     assert np.abs(res.traj[..., 2] - g["traj_speed"]).max() < 1e-9
 
 
+def test_plan_matches_the_reference_run_with_other_constants(golden):
+    """tests/golden/frenet_alt.npz: the reference planner run with 28 candidates of 14 / 15 points, tighter
+    limits, two obstacles considered (tools/make_golden_frenet.py --alt)."""
+    a = golden("frenet_alt")
+    p = params_from_golden(a, fr.frenet_params)
+    b = golden_batch(a)
+    res = fr.frenet_plan(_routes_from(b), b["path_id"], b["start"], b["ego_xy"], b["obs"], b["n_obs"], p, want_paths=True)
+    assert np.array_equal(res.index, a["index"])
+    assert np.array_equal(res.n_valid, a["n_valid"])
+    assert np.array_equal(res.feasible, a["feasible"]) and np.array_equal(res.collision_free, a["collision_free"])
+    assert np.abs(res.cost - a["cost"]).max() / np.abs(a["cost"]).max() < 1e-11
+    m = ~np.isnan(a["x"])
+    assert np.array_equal(np.isnan(res.paths[..., 0]), ~m)
+    assert np.abs(res.paths[..., 0][m] - a["x"][m]).max() < 1e-8 and np.abs(res.paths[..., 1][m] - a["y"][m]).max() < 1e-8
+    sm = ~np.isnan(a["traj_speed"])
+    assert np.array_equal(np.isnan(res.traj[..., 2]), ~sm)
+    assert np.abs(res.traj[..., 2][sm] - a["traj_speed"][sm]).max() < 1e-8
+
+
 def _against_oracle(n, n_paths, seed, params_kw=None, max_obs=6):
     rng = np.random.default_rng(seed)
     knots, off = synth_routes(rng, n_paths)

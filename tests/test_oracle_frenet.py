@@ -65,3 +65,26 @@ def test_near_tied_costs_are_reported_not_hidden(g):
     b = golden_batch(g, cport.spline_build)
     out = cport.frenet_plan(b["coef"], b["knot_off"], b["path_id"], b["start"], b["ego_xy"], b["obs"], b["n_obs"], p)
     assert np.abs(out["cost"][-1] - c).max() < 1e-10 and out["index"][-1] == g["index"][-1] == 6
+
+
+def test_other_planner_constants_match_the_reference(golden):
+    """The same scenarios run through the reference with other module constants (7 offsets x 2 horizons x
+    2 speeds = 28 candidates of 14 and 15 points, tighter speed / acceleration / curvature limits, two
+    obstacles considered, wider circles): tests/golden/frenet_alt.npz (make_golden_frenet.py --alt)."""
+    a = golden("frenet_alt")
+    p = params_from_golden(a, cport.frenet_params)
+    assert (p.n_d, p.n_T, p.n_v) == (7, 2, 2) and list(p.n_t[:2]) == [14, 15] and p.obstacles_considered == 2
+    b = golden_batch(a, cport.spline_build)
+    out = cport.frenet_plan(b["coef"], b["knot_off"], b["path_id"], b["start"], b["ego_xy"], b["obs"], b["n_obs"], p)
+    assert np.array_equal(out["index"], a["index"])
+    assert np.array_equal(out["n_valid"], a["n_valid"])
+    assert np.array_equal((out["flags"] & 1) != 0, a["feasible"])
+    assert np.array_equal((out["flags"] & 2) != 0, a["collision_free"])
+    assert np.abs(out["cost"] - a["cost"]).max() / np.abs(a["cost"]).max() < 1e-12
+    m = ~np.isnan(a["x"])
+    assert np.array_equal(np.isnan(out["paths"][..., 0]), ~m)
+    assert np.abs(out["paths"][..., 0][m] - a["x"][m]).max() < 1e-9 and np.abs(out["paths"][..., 1][m] - a["y"][m]).max() < 1e-9
+    sm = ~np.isnan(a["traj_speed"])
+    assert np.array_equal(np.isnan(out["traj"][..., 2]), ~sm)
+    assert np.abs(out["traj"][..., 2][sm] - a["traj_speed"][sm]).max() < 1e-9
+    assert (~a["feasible"]).sum() > 100 and (~a["collision_free"]).sum() > 100 and (a["index"] == 0).sum() >= 5

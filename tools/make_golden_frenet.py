@@ -87,7 +87,14 @@ def run_one(dm):
     # start state as the planner derived it (calculate_start_state :248-276)
     st = pl.calculate_start_state(dm)
     nc = len(cands)
-    nt = len(cands[0][0].t)
+    nt = max(len(c[0].t) for c in cands)
+
+    def ragged(key):
+        out = np.full((nc, nt), np.nan)
+        for i, c in enumerate(cands):
+            v = getattr(c[0], key)
+            out[i, :len(v)] = v
+        return out
     out = dict(
         knots_x=np.asarray(pl.ref_path[:, 0]), knots_y=np.asarray(pl.ref_path[:, 1]),
         spline_s=np.asarray(pl.csp.s, np.float64),
@@ -101,8 +108,8 @@ def run_one(dm):
         cost=np.array([c[1] for c in cands]),
         n_valid=np.array([len(c[0].x) for c in cands]),
         x=np.full((nc, nt), np.nan), y=np.full((nc, nt), np.nan),
-        s=np.array([c[0].s for c in cands]), d=np.array([c[0].d for c in cands]),
-        s_d=np.array([c[0].s_d for c in cands]), s_dd=np.array([c[0].s_dd for c in cands]),
+        s=ragged("s"), d=ragged("d"), s_d=ragged("s_d"), s_dd=ragged("s_dd"),
+        n_t=np.array([len(c[0].t) for c in cands]),
         n_pred=len(pl.obs_prediction.predict_paths[0].t) if pl.obs_prediction.predict_paths else 0,
     )
     for i, c in enumerate(cands):
@@ -119,16 +126,26 @@ def run_one(dm):
     out["traj_xy"] = np.full((nt, 2), np.nan)
     out["traj_xy"][:len(traj.x), 0] = traj.x
     out["traj_xy"][:len(traj.x), 1] = traj.y
-    out["traj_speed"] = np.asarray(traj.s_d, np.float64)
+    out["traj_speed"] = np.full(nt, np.nan)
+    out["traj_speed"][:len(traj.s_d)] = traj.s_d
     return out
 
 
-def main():
+ALT = dict(MAX_LEFT_WIDTH=-3, MAX_RIGHT_WIDTH=3, D_ROAD_W=1, MAXT=4.5, MAX_SPEED=11.0, MAX_ACCEL=2.0, MAX_CURVATURE=0.5,
+           OBSTACLES_CONSIDERED=2, ROBOT_RADIUS=2, KD=3.0, KJ=0.3)
+
+
+def main(alt=False):
+    """alt=True: the same scenarios with other module constants (7 offsets x 2 horizons x 2 speeds,
+    tighter limits, 2 obstacles considered, wider circles) -> frenet_alt.npz."""
+    if alt:
+        for k, v in ALT.items():
+            setattr(jtp, k, v)
     rng = np.random.default_rng(20240611)
     cases = []
     for kind in range(4):
         line = route(kind)
-        for j in range(16):
+        for j in range(16 if not alt else 10):
             near = j % 4 != 3
             n_obs = [3, 3, 0, 6, 1, 3, 4, 3, 2, 5, 3, 3, 6, 6, 4, 3][j]
             along = rng.uniform(0.02, 0.55 if kind != 3 else 0.75)
@@ -164,7 +181,7 @@ def main():
     pack["lane_xy"] = pad("lane_xy", max(len(c["lane_xy"]) for c in cases))
     pack["n_lane"] = np.array([len(c["lane_xy"]) for c in cases])
     pack["n_obs"] = np.array([len(c["obs"]) for c in cases])
-    for k in ("start", "ego_xy", "ego_v", "cost", "n_valid", "x", "y", "s", "d", "s_d", "s_dd", "feasible", "collision_free",
+    for k in ("start", "ego_xy", "ego_v", "cost", "n_valid", "n_t", "x", "y", "s", "d", "s_d", "s_dd", "feasible", "collision_free",
               "index", "traj_xy", "traj_speed", "route", "n_pred"):
         pack[k] = np.stack([np.asarray(c[k]) for c in cases])
     # the module constants the run used (JunctionTrajectoryPlanner.py:13-41)
@@ -172,12 +189,12 @@ def main():
               "MINT", "TARGET_SPEED", "D_T_S", "N_S_SAMPLE", "OBSTACLES_CONSIDERED", "ROBOT_RADIUS", "MOVE_GAP",
               "KJ", "KT", "KD", "KLAT", "KLON"):
         pack["const_" + k] = np.float64(getattr(jtp, k))
-    np.savez_compressed(os.path.join(OUT, "frenet.npz"), **pack)
+    np.savez_compressed(os.path.join(OUT, "frenet_alt.npz" if alt else "frenet.npz"), **pack)
     idx = pack["index"]
     print(f"{n} scenarios; selected index histogram {np.bincount(idx, minlength=11).tolist()}; "
-          f"truncated candidates {(pack['n_valid'] < pack['x'].shape[2]).sum()}; "
+          f"truncated candidates {(pack['n_valid'] < pack['n_t']).sum()}; "
           f"infeasible {(~pack['feasible']).sum()}; colliding {(~pack['collision_free']).sum()}; n_pred {set(pack['n_pred'].tolist())}")
 
 
 if __name__ == "__main__":
-    main()
+    main(alt="--alt" in sys.argv)
