@@ -260,7 +260,6 @@ __global__ void __launch_bounds__(kFrWarpsPerCta * 32) k_frenet_plan(const Frene
     if (sc >= a.n) return;
 
     const int n_lat = p.n_d * p.n_T, n_lon = p.n_T * p.n_v, C = n_lat * p.n_v;
-    const int n_circ_max = 2 * p.obstacles_considered;
     double *lat = reinterpret_cast<double *>(smem_raw + (size_t)warp * warp_bytes);
     double *lon = lat + n_lat * 6;
     double *X = lon + n_lon * 5;
@@ -460,7 +459,6 @@ __global__ void __launch_bounds__(kFrWarpsPerCta * 32) k_frenet_plan(const Frene
             o[2] = it < pick_nt ? (best >= 0 ? lo[1] + 2 * lo[2] * t + 3 * lo[3] * t2 + 4 * lo[4] * t2 * t : 0.0) : CUDART_NAN;
         }
     }
-    (void)n_circ_max;
 }
 
 }  // namespace dcarl
@@ -546,11 +544,8 @@ extern "C" int dcarl_frenet_plan(const double *coef, const int64_t *knot_off, in
     a.n = n; a.n_paths = n_paths; a.max_obs = max_obs;
     const size_t wb = (frenet_warp_bytes(p->n_d * p->n_T, p->n_T * p->n_v, C, Tm, 2 * p->obstacles_considered) + 15) & ~(size_t)15;
     const size_t smem = wb * kFrWarpsPerCta;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024)
         DCARL_CUDA(cudaFuncSetAttribute(k_frenet_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const long long grid = (n + kFrWarpsPerCta - 1) / kFrWarpsPerCta;
     k_frenet_plan<<<(unsigned)grid, kFrWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(a, *p, Tm, (unsigned)wb);
     DCARL_LAUNCH_CHECK("k_frenet_plan");

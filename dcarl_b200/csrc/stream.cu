@@ -799,12 +799,9 @@ static int launch_rows_ff(const StreamArgs &a, cudaStream_t st) {
     const int wpc = pick_warps_per_cta(a.n_inst, wb, sm_count());
     const size_t smem = kRowsCtaFixedBytes + wb * wpc;
     auto kern = k_stream_rows<RT, OT, OV, FF>;
-    static size_t configured = 0;   // per template instance; growing only
-    if (smem > configured) {
-        DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
-        DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = kMaxSmemPerCta;
-    }
+    // per launch, not cached: the attribute belongs to the current device's context
+    DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
+    DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     // the kernel indexes rows with 32 bits: launch in instance chunks of < 2^32 rows each
     const long long max_inst = a.n_steps ? (long long)(0xffffff00u / a.n_steps) : a.n_inst;
     for (long long lo = 0; lo < a.n_inst; lo += max_inst) {
