@@ -1,0 +1,59 @@
+"""Static properties of the built library's SASS (cuobjdump, no GPU needed) that the measured
+performance depends on: the stream kernel's main loop is free of divergence fallbacks (its control
+flow is provably warp-uniform), stays within 72 registers without spilling (28 warps per SM), and the
+kernels use the instructions DESIGN.md says they do."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from dcarl_b200 import _abi
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+
+def _sass(symbol_part):
+    out = subprocess.run(["cuobjdump", "-sass", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    keep, on = [], False
+    for line in out.splitlines():
+        if "Function :" in line:
+            on = symbol_part in line
+        elif on:
+            m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", line)
+            if m:
+                keep.append((int(m.group(1), 16), m.group(2).strip()))
+    assert keep, f"{symbol_part} not found in {_abi.LIB_PATH}"
+    return keep
+
+
+@pytest.fixture(scope="module")
+def rows_sass():
+    return _sass("k_stream_rowsIffLb1ELb0E")        # float rows, float outputs, overall on, priors' argmax = rule
+
+
+def test_stream_main_loop_is_warp_uniform(rows_sass):
+    # the main loop = the longest backward uniform branch
+    back = [(a, int(re.search(r"0x([0-9a-f]+)", s).group(1), 16)) for a, s in rows_sass if s.startswith("BRA.U UP")]
+    back = [(a, t) for a, t in back if t < a]
+    end, start = max(back, key=lambda x: x[0] - x[1])
+    loop = [s for a, s in rows_sass if start <= a <= end]
+    assert len(loop) > 500
+    assert not [s for s in loop if "BRA.DIV" in s], "divergence fallbacks are back in the stream kernel's main loop"
+    assert sum("MATCH.ANY" in s for s in loop) == 2 and sum(s.startswith("LDG") or " LDG" in s for s in loop) == 3
+    assert any("REDUX" in s for s in loop)                       # exact top-2 of the replay path
+    assert any("MUFU.RSQ64H" in s for s in loop)                 # 1/sqrt seeds of the bound
+
+
+def test_register_budget_of_the_row_kernel():
+    out = subprocess.run(["cuobjdump", "-res-usage", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    rows = re.findall(r"Function (\S*k_stream_rows\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert len(rows) == 16                                       # RT x OT x overall x force-first
+    for name, reg, stack in rows:
+        assert int(reg) <= 72 and int(stack) == 0, (name, reg, stack)   # 28 warps per SM, nothing spilled
+
+
+def test_box_scan_uses_bulk_copies():
+    sass = [s for _, s in _sass("k_box_momentsILi20E")]
+    assert any("UBLKCP" in s for s in sass)                      # 1-D TMA tile loads
+    assert any("SYNCS" in s for s in sass)                       # mbarrier arrive / wait
