@@ -66,6 +66,19 @@ def test_argument_validation_needs_no_device():
     assert L.dcarl_stream_bounds(None, None, None, 0, 0, 10, 20, 11, p, None, 0, None, None, None, None, None, None, 0, 0, None) == 0
     assert L.dcarl_box_select(None, 0, 8, _abi.RlsParams(), None, None, None) == 0
     assert L.dcarl_stream_bounds_ws(4096, 20000, 20, 11) >= 4096 * 220 * 28
+    assert L.dcarl_stream_rows_fit(20, 11) == 1 and L.dcarl_stream_rows_fit(40, 256) == 0
+    # the planner entry points validate their arguments on the host, before any launch
+    fp = _abi.FrenetParams()
+    L.dcarl_default_frenet_params(fp)
+    assert (fp.n_d, fp.n_T, fp.n_v, fp.n_t[0], fp.n_pred) == (5, 1, 2, 14, 15) and abs(fp.target_speed - 30 / 3.6) < 1e-15
+    assert L.dcarl_frenet_plan(None, None, 0, None, None, None, None, None, 0, 0, fp, None, None, None, None, None, None, None, None) == 0
+    fp.n_d = 17
+    assert L.dcarl_frenet_plan(None, None, 0, None, None, None, None, None, 0, 5, fp, None, None, None, None, None, None, None, None) == -11
+    assert b"n_d" in L.dcarl_last_error()
+    fp.n_d, fp.n_v = 16, 8
+    assert L.dcarl_frenet_plan(None, None, 0, None, None, None, None, None, 0, 5, fp, None, None, None, None, None, None, None, None) == -11
+    assert b"32 candidates" in L.dcarl_last_error()
+    assert L.dcarl_spline_build(None, None, 0, None, None) == 0 and L.dcarl_frenet_start(None, None, 0, None, None, 0, None, None) == 0
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_the_oracle():
