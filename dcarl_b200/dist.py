@@ -75,3 +75,29 @@ def stream_sharded(plan, idx, act, R, group=None):
     res = plan.run_device(idx, act, R)
     allreduce_stats(res.stats, group)
     return res, res.stats
+
+
+def frenet_stats(index, cost):
+    """Summary vector of one planning tick, float64 [3 + C + 1]: scenarios, brake ticks (index 0), summed
+    cost of the selected candidates, histogram of the selected index 0..C.  Tensor ops only (any device)."""
+    idx = index.long()
+    C = cost.shape[1]
+    hist = torch.bincount(idx.clamp_min(0), minlength=C + 1)[:C + 1].to(torch.float64)
+    picked = idx > 0
+    sel_cost = cost.gather(1, (idx - 1).clamp_min(0)[:, None])[:, 0].to(torch.float64)
+    head = torch.stack([torch.tensor(float(idx.numel()), dtype=torch.float64, device=idx.device),
+                        (idx == 0).sum().to(torch.float64), (sel_cost * picked).sum()])
+    return torch.cat([head, hist])
+
+
+def frenet_sharded(routes, path_id, ego, obs, n_obs, params=None, group=None):
+    """Planner pattern: scenarios are block-partitioned over ranks (the arguments are this rank's shard,
+    see ``shard_range``; the routes are replicated), each rank projects its egos and plans its scenarios with
+    no data-path exchange, and the summary vector of ``frenet_stats`` is all-reduced once.
+    Returns (this rank's FrenetResult, all-reduced stats).  ego [n, 5] = x, y, vx, vy, v (CUDA tensors)."""
+    from .frenet import frenet_plan, frenet_start
+    start = frenet_start(routes, path_id, ego)
+    res = frenet_plan(routes, path_id, start, ego[:, :2].contiguous(), obs, n_obs, params)
+    stats = frenet_stats(res.index, res.cost)
+    allreduce_stats(stats, group)
+    return res, stats

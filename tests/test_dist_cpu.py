@@ -108,3 +108,55 @@ def test_row_sharded_box_moments_sum_to_the_unsharded_answer(golden):
     var = np.where(n > 0, np.maximum(tot[:, :, 2] / np.maximum(n, 1) - mean ** 2, 0.0), -1.0)
     assert np.abs(mean - full[:, :, 1]).max() < 1e-12 and np.abs(var - full[:, :, 2]).max() < 1e-12
     assert np.array_equal(cport.box_select(np.stack([n, mean, var], -1)), cport.box_select(full))
+
+
+def _frenet_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from dcarl_b200 import dist as ddist
+    from helpers_frenet import synth_routes, synth_scenarios
+    from oracle import cport
+    ddist.init_from_env(backend="gloo")
+    rng = np.random.default_rng(31)                      # same seed on every rank: same global batch
+    knots, off = synth_routes(rng, 5)
+    pid, start, ego, obs, n_obs = synth_scenarios(rng, 301, knots, off)
+    coef = np.concatenate([cport.spline_build(knots[off[i]:off[i + 1]]) for i in range(5)])
+    lo, hi = ddist.shard_range(301, rank, world)
+    out = cport.frenet_plan(coef, off, pid[lo:hi], start[lo:hi], ego[lo:hi], obs[lo:hi], n_obs[lo:hi], cport.frenet_params())
+    st = ddist.frenet_stats(torch.from_numpy(out["index"]), torch.from_numpy(out["cost"]))
+    ddist.allreduce_stats(st)
+    ddist.barrier()
+    q.put((rank, lo, hi, st.numpy(), out["index"]))
+    tdist.destroy_process_group()
+
+
+def test_two_rank_planner_shards_and_stats_allreduce():
+    """Row f3 on N > 1: scenarios block-partitioned, no exchange, one all-reduce of the tick's summary."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dcarl_b200 import dist as ddist
+    from helpers_frenet import synth_routes, synth_scenarios
+    from oracle import cport
+    rng = np.random.default_rng(31)
+    knots, off = synth_routes(rng, 5)
+    pid, start, ego, obs, n_obs = synth_scenarios(rng, 301, knots, off)
+    coef = np.concatenate([cport.spline_build(knots[off[i]:off[i + 1]]) for i in range(5)])
+    whole = cport.frenet_plan(coef, off, pid, start, ego, obs, n_obs, cport.frenet_params())
+    want = ddist.frenet_stats(torch.from_numpy(whole["index"]), torch.from_numpy(whole["cost"])).numpy()
+    assert want[0] == 301 and want[3:].sum() == 301 and want[1] == (whole["index"] == 0).sum()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_frenet_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == 0 and got[0][2] == got[1][1] and got[1][2] == 301
+    for _, lo, hi, st, index in got:
+        assert np.array_equal(index, whole["index"][lo:hi])           # per-scenario results do not depend on the sharding
+        assert np.array_equal(st[[0, 1]], want[[0, 1]]) and np.array_equal(st[3:], want[3:])   # counts: exact
+        assert abs(st[2] - want[2]) <= 1e-9 * abs(want[2])

@@ -76,6 +76,30 @@ out["box_counts_identical"] = bool(torch.equal(mom[:, :, 0], mom1[:, :, 0]))
 out["box_sums_max_rel_diff"] = float(((mom - mom1).abs() / mom1.abs().clamp_min(1e-9)).max())
 out["box_picks_identical"] = bool(torch.equal(pick, pick1))
 
+# ---- (iii) planner (row f3), scenario-sharded ------------------------------------------------------
+import bench  # noqa: E402  (synthetic planner inputs: same seed on every rank = same global batch)
+n_sc = 20000
+knots, off, pid, start_unused, ego_xy, obs, n_obs = bench.synth_frenet(n_sc, 16, 6000)
+rng = np.random.default_rng(6001)
+ego = np.concatenate([ego_xy, rng.normal(0, 4, (n_sc, 2)), rng.uniform(0.2, 12, (n_sc, 1))], axis=1)   # x, y, vx, vy, v
+routes = dc.Routes(knots)
+tt = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+lo, hi = dd.shard_range(n_sc, rank, world)
+mine, st_f = dd.frenet_sharded(routes, tt(pid[lo:hi], torch.int32), tt(ego[lo:hi], torch.float64), tt(obs[lo:hi], torch.float64),
+                               tt(n_obs[lo:hi], torch.int32))
+d_ego = tt(ego, torch.float64)
+whole_f = dc.frenet_plan(routes, tt(pid, torch.int32), dc.frenet_start(routes, tt(pid, torch.int32), d_ego), d_ego[:, :2].contiguous(),
+                         tt(obs, torch.float64), tt(n_obs, torch.int32))
+want = dd.frenet_stats(whole_f.index, whole_f.cost)
+torch.cuda.synchronize()
+ok = bool(torch.equal(mine.index, whole_f.index[lo:hi]) and torch.equal(mine.cost, whole_f.cost[lo:hi])
+          and torch.equal(mine.traj_len, whole_f.traj_len[lo:hi]))
+ok = ok and bool(torch.equal(st_f[:2], want[:2]) and torch.equal(st_f[3:], want[3:])) and \
+    float((st_f[2] - want[2]).abs() / want[2].abs().clamp_min(1)) < 1e-9
+flag = torch.tensor([float(ok)], device=dev, dtype=torch.float64)
+torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN) if world > 1 else None
+out["frenet_sharded_identical"] = bool(flag.item() == 1.0)
+
 # ---- timings: config 4 (1e7 rows over all GPUs) and config 5 (mixed, 32768 instances per GPU) ------
 if os.environ.get("TIMINGS", "1") == "1":
     M4 = 10_000_000 // world
