@@ -12,6 +12,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "lib", "libdcarl_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "dcarl_b200.h")
 _lib = None
+ABI_VERSION = 2
 
 
 class DcarlError(RuntimeError):
@@ -73,6 +74,8 @@ SIGNATURES = {
     "dcarl_stream_rows_fit": (_int, [_i32, _i32]),
     "dcarl_stream_bounds": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i32, _i32, C.POINTER(Params),
                                    _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
+    "dcarl_stream_bounds_u8": (_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(Params),
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcarl_cell_values": (_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Params), _vp, _vp]),
     "dcarl_stream_stats": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "dcarl_sample_returns": (_int, [_vp, _int, _vp, _vp, _int, _vp, _i64, _i32, _i32, _d, _d, _d, _d,
@@ -118,7 +121,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.dcarl_abi_version() != 1:
+        if L.dcarl_abi_version() != ABI_VERSION:
             raise RuntimeError("dcarl_b200: ABI version mismatch between _abi.py and the built library")
         _lib = L
     return _lib

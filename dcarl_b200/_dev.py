@@ -7,7 +7,8 @@ import torch
 from . import _abi
 
 _NP2T = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
-         np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
+         np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+         np.dtype(np.uint8): torch.uint8}
 
 
 def require_cuda():

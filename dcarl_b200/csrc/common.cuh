@@ -51,6 +51,11 @@ __device__ __forceinline__ int ld_stream(const int *p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint8_t ld_stream(const uint8_t *p) {
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (uint8_t)v;
+}
 __device__ __forceinline__ float ld_stream(const float *p) {
     float v;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
@@ -63,6 +68,9 @@ __device__ __forceinline__ double ld_stream(const double *p) {
 }
 __device__ __forceinline__ void st_stream(int *p, int v) {
     asm volatile("st.global.L1::no_allocate.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream(uint8_t *p, uint8_t v) {
+    asm volatile("st.global.L1::no_allocate.u8 [%0], %1;" ::"l"(p), "r"((unsigned)v) : "memory");
 }
 __device__ __forceinline__ void st_stream(float *p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");

@@ -31,11 +31,11 @@
 namespace dcarl {
 
 struct StreamArgs {
-    const int *idx;
-    const int *act;
+    const void *idx;   // int32, or uint8 in the compact wire format
+    const void *act;
     const void *R;
     void *out_value;
-    int *out_act;
+    void *out_act;
     long long *out_activation;
     void *out_overall;
     unsigned long long *act_hist;
@@ -68,31 +68,37 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
 
 // Value of a cell holding n samples with sum s1 and sum of squares s2, given
-// rs = 1/sqrt(n) and rs1 = 1/sqrt(n+1).
+// rs = 1/sqrt(n), rs1 = 1/sqrt(n+1) and dn50 = n * 2^-50.
 //   rule action:  min(cap, mean + scale*sqrt(L/2/n))                       ST1:12
 //   other:        min(mean - scale*sqrt(L/2/n),                            ST1:16
 //                     sum/n/(n+1) - 4*std/(n+1) + sum/(n+1) - scale*sqrt(L/2/(n+1)))   ST1:24
 // evaluated in float64 (a few ulp from the reference's divide/sqrt chain, far inside
 // the 1e-5 value tolerance; the argmax only flips on ties closer than ~1e-11).
-__device__ __forceinline__ double cell_value_rs(double rs, double rs1, double s1, double s2, bool is_rule,
-                                                double c_h, double cap) {
+// The variance comes from one-pass moments, s2/n - mean^2, whose rounding error is bounded by
+// (3n + 4) 2^-53 mean^2: anything at or below 8n 2^-53 mean^2 is indistinguishable from a constant
+// cell and gives sigma = 0 exactly, like the reference's two-pass np.std on constant samples.
+__device__ __forceinline__ double cell_value_rs(double rs, double rs1, double dn50, double s1, double s2,
+                                                bool is_rule, double c_h, double cap) {
     const double inv_n = rs * rs;
-    const double hn = c_h * rs;
     const double mean = s1 * inv_n;
-    const double ub = dmin(cap, mean + hn);
+    // +c_h for the rule action (upper bound), -c_h otherwise (lower bound): one fma serves both
+    const double c_s = __hiloint2double(__double2hiint(c_h) ^ (is_rule ? 0 : (int)0x80000000), __double2loint(c_h));
+    const double x = fma(rs, c_s, mean);
     const double inv_n1 = rs1 * rs1;
     const double hn1 = c_h * rs1;
-    const double var = fma(s2, inv_n, -mean * mean);
-    const double sigma = var > 1e-280 ? var * rsqrt_pos(var) : 0.0;
-    const double lb = mean - hn;
+    const double t = mean * mean;
+    const double var = fma(s2, inv_n, -t);
+    const double sigma = var > t * dn50 ? var * rsqrt_pos(var) : 0.0;
     const double ci = fma(fma(-4.0, sigma, mean) + s1, inv_n1, -hn1);
-    return is_rule ? ub : dmin(lb, ci);
+    return dmin(x, is_rule ? cap : ci);
 }
 
 __device__ __forceinline__ double cell_value(unsigned n, double s1, double s2, bool is_rule, double c_h,
                                              double cap) {
     const double dn = u32_to_double(n);
-    return cell_value_rs(rsqrt_pos(dn), rsqrt_pos(dn + 1.0), s1, s2, is_rule, c_h, cap);
+    // n * 2^-50, exact: the same bit trick with the exponent lowered by 50
+    const double dn50 = __hiloint2double(0x43300000 - (50 << 20), (int)n) - 4.0;
+    return cell_value_rs(rsqrt_pos(dn), rsqrt_pos(dn + 1.0), dn50, s1, s2, is_rule, c_h, cap);
 }
 
 // Runner-up bound kept per state: any value in [second, max) keeps both fast-path tests
@@ -201,23 +207,47 @@ __device__ __forceinline__ double scan_step(double x, int off) {
     return r;
 }
 
-struct Cell {
-    double s1, s2, val;
+// Per-instance tables of the row kernel (shared memory).  Every record is laid out for the widest
+// access the access pattern allows: random gathers by 32 lanes cost one wavefront per conflicting
+// bank group, and 16-byte accesses (8 lanes per wavefront) lose the least to such conflicts — the
+// kernel's first limiter is the shared-memory data pipe (profiles/).
+struct __align__(16) Mom2 {
+    double s1, s2;   // running sum and sum of squares of the cell's returns
 };
-// per-state records, split so that the hot pair is one conflict-friendly 16-byte load
+// Per-state record: one 16-byte load per row.  The low 16 mantissa bits of `sub2` carry the state's
+// argmax (15 bits) and its "activated" flag (bit 15), see pack_bound().
 struct __align__(16) StateHot {
     double smax;   // current max_a value[s][a]
-    double sub2;   // runner-up bound: second-best <= sub2 < smax (== smax on an exact tie)
+    double sub2;   // runner-up bound: second-best <= sub2 (and < smax unless the top two are closer than ~1e-11)
 };
-struct __align__(8) StateArg {
-    int sarg;      // current first argmax
-    int actstep;   // activation step, -1 = not yet (ST1:58)
-};
+
+constexpr unsigned kArgMask = 0x7fffu, kActivatedBit = 0x8000u;
+
+// A bound >= b whose low 16 mantissa bits are `payload`.  Any value >= the true second-best keeps
+// the selector's fast path sound (a looser bound only sends more rows to the exact path), so the
+// bound is moved up by less than 2^17 ulp to make room.
+__device__ __forceinline__ double pack_bound(double b, unsigned payload) {
+    long long bits = __double_as_longlong(b);
+    const bool neg = bits < 0;
+    unsigned long long mag = (unsigned long long)bits & 0x7fffffffffffffffull;
+    if (neg) {
+        // towards zero: drop the low bits and one more unit, so that adding the payload stays above b
+        if (mag > 0x7fefffffffffffffull) mag = 0x7fefffffffffffffull;     // -inf (a single action): -DBL_MAX
+        const unsigned long long hi = mag >> 16;
+        if (hi == 0) return __longlong_as_double((long long)payload);     // within 2^-1022 of zero: a tiny positive
+        mag = ((hi - 1) << 16) | payload;
+        return __longlong_as_double((long long)(mag | 0x8000000000000000ull));
+    }
+    unsigned long long hi = (mag >> 16) + 1;                               // away from zero
+    if (hi > (0x7fefffffffffffffull >> 16)) hi = 0x7fefffffffffffffull >> 16;
+    return __longlong_as_double((long long)((hi << 16) | payload));
+}
+__device__ __forceinline__ unsigned bound_payload(double sub2) { return (unsigned)__double2loint(sub2) & 0xffffu; }
 
 __host__ __device__ inline size_t rows_warp_bytes(int S, int A) {
     const size_t ncell = (size_t)S * A;
-    size_t b = (size_t)S * (sizeof(StateHot) + sizeof(StateArg) + sizeof(int))   // hot, arg, flushpt
-               + ncell * sizeof(Cell) + ncell * sizeof(unsigned)                   // cells, cnt
+    size_t b = (size_t)S * (sizeof(StateHot) + 2 * sizeof(int))                    // hot, actstep, flushpt
+               + ncell * (sizeof(Mom2) + sizeof(double) + sizeof(unsigned))        // moments, val, cnt
                + (size_t)A * sizeof(unsigned);                                     // per-warp action histogram
     return (b + 15) & ~(size_t)15;
 }
@@ -249,7 +279,7 @@ __device__ __forceinline__ void peer_masks(int s, int a, unsigned &ms, unsigned 
 __device__ unsigned long long g_rows_timing[4 * 65536];   // per instance: start ns, end ns, smid, hw warp id
 #endif
 
-template <typename RT, typename OT, bool OVERALL, bool FORCE_FIRST>
+template <typename RT, typename OT, typename KT, bool OVERALL, bool FORCE_FIRST>
 __global__ void __launch_bounds__(kRowsMaxWarps * 32, 1)
 k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -263,26 +293,25 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
 
     const int S = p.S, A = p.A, ncell = S * A;
     StateHot *hot = reinterpret_cast<StateHot *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
-    StateArg *sargs = reinterpret_cast<StateArg *>(hot + S);
-    Cell *cells = reinterpret_cast<Cell *>(sargs + S);
-    unsigned *cnt = reinterpret_cast<unsigned *>(cells + ncell);
-    int *flushpt = reinterpret_cast<int *>(cnt + ncell);
+    Mom2 *mom2 = reinterpret_cast<Mom2 *>(hot + S);
+    double *val = reinterpret_cast<double *>(mom2 + ncell);
+    unsigned *cnt = reinterpret_cast<unsigned *>(val + ncell);
+    int *actstep = reinterpret_cast<int *>(cnt + ncell);       // activation step per state, -1 = not yet (ST1:58)
+    int *flushpt = actstep + S;
     unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
 
     for (int c = lane; c < ncell; c += 32) {
-        cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
-        cells[c].val = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
+        mom2[c].s1 = 0.0; mom2[c].s2 = 0.0; cnt[c] = 0u;
+        val[c] = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
     }
     for (int a = lane; a < A; a += 32) hist[a] = 0u;
     __syncwarp();
     {
         double m0, sec0; int g0;
-        warp_top2(&cells[0].val, 3, A, m0, g0, sec0);
+        warp_top2(val, 1, A, m0, g0, sec0);
         StateHot h0;
-        h0.smax = m0; h0.sub2 = runner_up_bound(sec0, m0);
-        StateArg a0;
-        a0.sarg = g0; a0.actstep = -1;                                          // ST1:58
-        for (int s = lane; s < S; s += 32) { hot[s] = h0; sargs[s] = a0; flushpt[s] = 0; }
+        h0.smax = m0; h0.sub2 = pack_bound(runner_up_bound(sec0, m0), (unsigned)g0);
+        for (int s = lane; s < S; s += 32) { hot[s] = h0; actstep[s] = -1; flushpt[s] = 0; }
     }
     __syncwarp();
 
@@ -304,20 +333,20 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     const unsigned n_thres = (unsigned)p.n_thres;
     constexpr bool SCAN_F32 = std::is_same<OT, float>::value;
 
-    const int *__restrict__ gidx = p.idx;
-    const int *__restrict__ gact = p.act;
+    const KT *__restrict__ gidx = reinterpret_cast<const KT *>(p.idx);
+    const KT *__restrict__ gact = reinterpret_cast<const KT *>(p.act);
     const RT *__restrict__ gR = reinterpret_cast<const RT *>(p.R);
     OT *__restrict__ oval = reinterpret_cast<OT *>(p.out_value);
-    int *__restrict__ oact = p.out_act;
+    KT *__restrict__ oact = reinterpret_cast<KT *>(p.out_act);
     OT *__restrict__ oall = reinterpret_cast<OT *>(p.out_overall);
     const unsigned ebase = (unsigned)inst * n_steps + lane;
 
     double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
-    unsigned clamped = 0;   // lane-local OR of (raw key ^ clamped key): non-zero once a row was out of range
+    unsigned nbad = 0;    // rows of this lane whose key was out of range
 
     int n_idx = 0, n_act = 0;
     RT n_R = RT(0);
-    if ((unsigned)lane < n_steps) { n_idx = ld_stream(gidx + ebase); n_act = ld_stream(gact + ebase); n_R = ld_stream(gR + ebase); }
+    if ((unsigned)lane < n_steps) { n_idx = (int)ld_stream(gidx + ebase); n_act = (int)ld_stream(gact + ebase); n_R = ld_stream(gR + ebase); }
 
     struct Rows {      // a batch after its moment stage
         int s, sx, a, kx;
@@ -345,22 +374,22 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     auto p1a_issue = [&](auto tail_tag, const unsigned k, Rows &r, Mom &m) {
         constexpr bool TAIL = decltype(tail_tag)::value;
         const bool in_stream = TAIL ? (k < n_steps) : true;
-        // out-of-range keys are clamped (memory safety) and remembered: the call then reports bad rows
-        // (lanes past the end of the stream re-read keys that were already checked)
+        // out-of-range keys are clamped (memory safety) and counted: the call then reports bad rows
+        // (lanes past the end of the stream re-read keys that were already counted)
         const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
         const int a = (int)min((unsigned)n_act, (unsigned)(A - 1));
-        clamped |= (unsigned)(n_idx ^ s_in) | (unsigned)(n_act ^ a);
+        if (in_stream && ((n_idx != s_in) | (n_act != a))) ++nbad;
         m.rin = n_R;
         const unsigned e = ebase + (k - lane);
-        if (k + 32 < n_steps) { n_idx = ld_stream(gidx + e + 32); n_act = ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
+        if (k + 32 < n_steps) { n_idx = (int)ld_stream(gidx + e + 32); n_act = (int)ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
         r.active = in_stream;
         r.s = in_stream ? s_in : (0x40000000 | lane);
         r.sx = in_stream ? s_in : 0;
         r.a = a;
         r.kx = in_stream ? s_in * A + a : 0;
         peer_masks(r.s, a, r.ms, r.mk);   // mk = action peers until p1a_peers
-        const Cell *cell = cells + r.kx;
-        m.acc1 = cell->s1; m.acc2 = cell->s2;
+        const Mom2 mm = mom2[r.kx];        // one 16-byte gather
+        m.acc1 = mm.s1; m.acc2 = mm.s2;
         r.n = cnt[r.kx];
     };
     // peers part: the cell mask, the row's sample count, the return of the oldest in-batch peer
@@ -388,20 +417,18 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         m.acc2 = fma(x, x, m.acc2);
         __syncwarp();   // every lane has read its cell
         if (r.active && (r.mk & gt) == 0) {
-            Cell *cell = cells + r.kx;
-            cnt[r.kx] = r.n; cell->s1 = m.acc1; cell->s2 = m.acc2;
+            Mom2 mm;
+            mm.s1 = m.acc1; mm.s2 = m.acc2;
+            cnt[r.kx] = r.n; mom2[r.kx] = mm;   // one 16-byte scatter
         }
         r.v = cell_value(r.n, m.acc1, m.acc2, r.a == rule, c_h, cap);
     };
 
-    // ---- selector stage: per-row (max, argmax) of the row's state; same logic as k_stream_rows
+    // ---- selector stage: per-row (max, argmax) of the row's state
     auto p2 = [&](const Rows &r, Sel &o) {
         const int lane_ = lane;
         StateHot *sh = hot + r.sx;
-        StateArg *sa = sargs + r.sx;
-        Cell *cell = cells + r.kx;
         StateHot h = *sh;
-        StateArg ga = *sa;
         const bool upd = r.active && r.n > n_thres;                               // ST1:86
         const double v = r.v;
         const int a = r.a;
@@ -414,7 +441,9 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         auto round = [&](auto first_tag) {
             constexpr bool FIRST = decltype(first_tag)::value;   // first round of the batch: every active row is pending
             const double c_ms0 = h.smax, c_ub = h.sub2;
-            const int c_g = ga.sarg;
+            const unsigned pl = bound_payload(c_ub);
+            const int c_g = (int)(pl & kArgMask);
+            const bool activated = (pl & kActivatedBit) != 0;
             const bool T = mine && upd && a == c_g;
             const unsigned tm = __ballot_sync(FULL_MASK, T);
             const unsigned cand = tm & ms & lt;
@@ -426,7 +455,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const bool gt_ub = v > c_ub, lt_mk = v < m_k;
             // A row of another cell that rises above the runner-up bound but stays below the max keeps
             // the argmax; it only lifts the bound that later argmax-cell rows of its state must clear.
-            const bool forced = FORCE_FIRST ? (mine & (ga.actstep == -1)) : false;
+            const bool forced = FORCE_FIRST ? (mine & !activated) : false;
             const bool lifter = mine & upd & !T & gt_ub & lt_mk & !forced;
             const unsigned lm = __ballot_sync(FULL_MASK, lifter);
             double B = c_ub;   // bound in force at this row: c_ub and the earlier lifters of its state
@@ -447,18 +476,20 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             __syncwarp();
             const bool done = mine & ((fin & bit) != 0);
             if (FIRST) {   // rows that are not done yet are overwritten by a later round or by their replay
-                o.g_out = c_g; o.m_out = m_k; o.mprev_out = m_prev; o.act_prev = ga.actstep != -1;
+                o.g_out = c_g; o.m_out = m_k; o.mprev_out = m_prev; o.act_prev = activated;
             } else {
                 o.g_out = done ? c_g : o.g_out;
                 o.m_out = done ? m_k : o.m_out;
                 o.mprev_out = done ? m_prev : o.mprev_out;
-                o.act_prev = done ? (ga.actstep != -1) : o.act_prev;
+                o.act_prev = done ? activated : o.act_prev;
             }
-            if (done & upd & ((mk & fin & gt) == 0)) cell->val = v;
+            if (done & upd & ((mk & fin & gt) == 0)) val[r.kx] = v;
+            // the state's max only moves when one of its finalized rows is on the argmax cell
             const bool last_of_state = done & ((ms & fin & gt) == 0);
-            if (last_of_state) sh->smax = m_k;
+            if (last_of_state & ((tm & ms & fin) != 0)) sh->smax = m_k;
             if (lm != 0) {     // rare: the last finalized row of a lifted state re-centres its bound
-                if (last_of_state & ((lm & ms & fin) != 0)) sh->sub2 = runner_up_bound((lifter & (v > B)) ? v : B, m_k);
+                if (last_of_state & ((lm & ms & fin) != 0))
+                    sh->sub2 = pack_bound(runner_up_bound((lifter & (v > B)) ? v : B, m_k), pl);
             }
         };
         round(std::true_type{});
@@ -469,40 +500,45 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 __syncwarp();
                 const int sj = __shfl_sync(FULL_MASK, r.s, j);
                 const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
-                if (lane_ == j && upd) cell->val = v;
+                if (lane_ == j && upd) val[r.kx] = v;
                 __syncwarp();
-                const StateArg oa = sargs[sj];
+                const unsigned opl = bound_payload(hot[sj].sub2);
+                const int o_arg = (int)(opl & kArgMask);
+                const bool o_activated = (opl & kActivatedBit) != 0;
                 double mx, second; int arg;
-                if (A <= 32) warp_top2_small(&cells[sj * A].val, 3, A, mx, arg, second);
-                else warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
+                if (A <= 32) warp_top2_small(val + sj * A, 1, A, mx, arg, second);
+                else warp_top2(val + sj * A, 1, A, mx, arg, second);
                 __syncwarp();   // every lane has read the state record and the values before lane j rewrites them
                 // The argmax only ever changes here, so a state can only activate here (ST1:98-99):
                 // between two exact rows "argmax != rule" implies "already activated".
-                const bool activates = oa.actstep == -1 && arg != rule;
-                if (arg != oa.sarg || activates) {
+                const bool activates = !o_activated && arg != rule;
+                if (arg != o_arg || activates) {
                     unsigned csum = 0;
                     for (int q = lane_; q < A; q += 32) csum += cnt[sj * A + q];
                     // 1-based count of this state's rows up to and including row j
                     const int t_j = (int)__reduce_add_sync(FULL_MASK, csum) - __popc(msj & ~((2u << j) - 1u));
                     if (lane_ == j) {
-                        if (arg != oa.sarg) {
+                        if (arg != o_arg) {
                             // rows (flushpt, t_j) of this state were emitted with the old argmax: account for them
-                            hist[oa.sarg] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1;
+                            hist[o_arg] += (unsigned)(t_j - 1 - flushpt[sj]); flushpt[sj] = t_j - 1;
                         }
-                        if (activates) { sa->actstep = t_j; o.jump = true; }
+                        if (activates) { actstep[sj] = t_j; o.jump = true; }
                     }
                     o.any_jump |= activates;
                 }
                 if (lane_ == j) {
-                    o.g_out = arg; o.m_out = mx; o.mprev_out = m_prev; o.act_prev = oa.actstep != -1;
-                    sh->smax = mx; sh->sub2 = runner_up_bound(second, mx); sa->sarg = arg;
+                    o.g_out = arg; o.m_out = mx; o.mprev_out = m_prev; o.act_prev = o_activated;
+                    StateHot nh;
+                    nh.smax = mx;
+                    nh.sub2 = pack_bound(runner_up_bound(second, mx),
+                                         (unsigned)arg | ((o_activated | activates) ? kActivatedBit : 0u));
+                    *sh = nh;
                 }
                 __syncwarp();
                 pend &= ~(fin | (1u << j));
                 mine = mine && lane_ > j;
                 if (pend == 0) break;
                 h = *sh;
-                ga = *sa;
                 round(std::false_type{});
                 if (fm == 0) break;
             }
@@ -516,7 +552,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         const unsigned e = ebase + (k - lane);
         if (in_stream) {
             st_stream(oval + e, (OT)o.m_out);
-            st_stream(oact + e, o.g_out);
+            st_stream(oact + e, (KT)o.g_out);
         }
         if (OVERALL) {
             // rows of states that were active before the row: the bonus cancels in after - before
@@ -592,18 +628,21 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         g_rows_timing[inst * 4 + 1] = t;
     }
 #endif
-    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)sargs[s].actstep;
+    for (int s = lane; s < S; s += 32) p.out_activation[inst * S + s] = (long long)actstep[s];
     if (p.act_hist != nullptr) {
         for (int s = lane; s < S; s += 32) {
             unsigned csum = 0;
             for (int q = 0; q < A; ++q) csum += cnt[s * A + q];
-            atomicAdd(&hist[sargs[s].sarg], csum - (unsigned)flushpt[s]);
+            atomicAdd(&hist[bound_payload(hot[s].sub2) & kArgMask], csum - (unsigned)flushpt[s]);
         }
         __syncwarp();
         for (int a = lane; a < A; a += 32)
             if (hist[a]) atomicAdd(p.act_hist + a, (unsigned long long)hist[a]);
     }
-    if (p.bad_rows != nullptr && clamped) atomicAdd(p.bad_rows, 1ull);
+    if (p.bad_rows != nullptr) {
+        const unsigned tot_bad = __reduce_add_sync(FULL_MASK, nbad);
+        if (lane == 0 && tot_bad) atomicAdd(p.bad_rows, (unsigned long long)tot_bad);
+    }
 }
 
 // ---- general-shape walker: tables in global memory, one row at a time ----------------------
@@ -652,7 +691,11 @@ __global__ void __launch_bounds__(128) k_stream_walk(const StreamArgs p, unsigne
         const long long k = k0 + lane;
         int b_idx = 0, b_act = 0;
         double b_r = 0.0;
-        if (k < n_steps) { b_idx = p.idx[row0 + k]; b_act = p.act[row0 + k]; b_r = (double)gR[k]; }
+        if (k < n_steps) {
+            b_idx = reinterpret_cast<const int *>(p.idx)[row0 + k];
+            b_act = reinterpret_cast<const int *>(p.act)[row0 + k];
+            b_r = (double)gR[k];
+        }
         double o_val = CUDART_NAN, o_all = 0.0;
         int o_act = -1;
         const int nrow = (int)min((long long)32, n_steps - k0);
@@ -699,7 +742,7 @@ __global__ void __launch_bounds__(128) k_stream_walk(const StreamArgs p, unsigne
         }
         if (k < n_steps) {
             oval[k] = (OT)o_val;
-            p.out_act[row0 + k] = o_act;
+            reinterpret_cast<int *>(p.out_act)[row0 + k] = o_act;
             if (OVERALL) oall[k] = (OT)o_all;
             if (p.act_hist != nullptr && o_act >= 0) atomicAdd(p.act_hist + o_act, 1ull);
         }
@@ -793,12 +836,12 @@ static bool priors_argmax_is_rule(const StreamArgs &a) {
     return a.A == 1;
 }
 
-template <typename RT, typename OT, bool OV, bool FF>
+template <typename RT, typename OT, typename KT, bool OV, bool FF>
 static int launch_rows_ff(const StreamArgs &a, cudaStream_t st) {
     const size_t wb = rows_warp_bytes(a.S, a.A);
     const int wpc = pick_warps_per_cta(a.n_inst, wb, sm_count());
     const size_t smem = kRowsCtaFixedBytes + wb * wpc;
-    auto kern = k_stream_rows<RT, OT, OV, FF>;
+    auto kern = k_stream_rows<RT, OT, KT, OV, FF>;
     // per launch, not cached: the attribute belongs to the current device's context
     DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
     DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -808,7 +851,9 @@ static int launch_rows_ff(const StreamArgs &a, cudaStream_t st) {
         StreamArgs c = a;
         c.n_inst = a.n_inst - lo < max_inst ? a.n_inst - lo : max_inst;
         const long long off = lo * (long long)a.n_steps;
-        c.idx = a.idx + off; c.act = a.act + off; c.out_act = a.out_act + off;
+        c.idx = reinterpret_cast<const KT *>(a.idx) + off;
+        c.act = reinterpret_cast<const KT *>(a.act) + off;
+        c.out_act = reinterpret_cast<KT *>(a.out_act) + off;
         c.R = reinterpret_cast<const RT *>(a.R) + off;
         c.out_value = reinterpret_cast<OT *>(a.out_value) + off;
         if (OV) c.out_overall = reinterpret_cast<OT *>(a.out_overall) + off;
@@ -820,9 +865,10 @@ static int launch_rows_ff(const StreamArgs &a, cudaStream_t st) {
     return 0;
 }
 
-template <typename RT, typename OT, bool OV>
+template <typename RT, typename OT, typename KT, bool OV>
 static int launch_rows(const StreamArgs &a, cudaStream_t st) {
-    return priors_argmax_is_rule(a) ? launch_rows_ff<RT, OT, OV, false>(a, st) : launch_rows_ff<RT, OT, OV, true>(a, st);
+    return priors_argmax_is_rule(a) ? launch_rows_ff<RT, OT, KT, OV, false>(a, st)
+                                    : launch_rows_ff<RT, OT, KT, OV, true>(a, st);
 }
 
 template <typename RT, typename OT, bool OV>
@@ -837,8 +883,8 @@ static int launch_walk(const StreamArgs &a, void *ws, cudaStream_t st) {
 template <typename RT, typename OT>
 static int dispatch_ov(const StreamArgs &a, bool rows, void *ws, cudaStream_t st) {
     if (a.out_overall)
-        return rows ? launch_rows<RT, OT, true>(a, st) : launch_walk<RT, OT, true>(a, ws, st);
-    return rows ? launch_rows<RT, OT, false>(a, st) : launch_walk<RT, OT, false>(a, ws, st);
+        return rows ? launch_rows<RT, OT, int, true>(a, st) : launch_walk<RT, OT, true>(a, ws, st);
+    return rows ? launch_rows<RT, OT, int, false>(a, st) : launch_walk<RT, OT, false>(a, ws, st);
 }
 
 }  // namespace dcarl
@@ -856,12 +902,10 @@ extern "C" int dcarl_stream_rows_fit(int32_t S, int32_t A) {
     return kRowsCtaFixedBytes + rows_warp_bytes(S, A) <= kMaxSmemPerCta ? 1 : 0;
 }
 
-extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const void *R, int r_is_f64,
-                                   int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
-                                   const dcarl_params *p, void *out_value, int out_is_f64,
-                                   int32_t *out_act, int64_t *out_activation_step, void *out_overall,
-                                   uint64_t *act_hist, uint64_t *bad_rows, void *ws, size_t ws_bytes,
-                                   int variant, dcarl_stream_t stream) {
+// Shared argument checks of the two stream entry points; fills `a` (everything but the row pointers).
+static int stream_args(int64_t n_inst, int64_t n_steps, int32_t S, int32_t A, const dcarl_params *p,
+                       int64_t *out_activation_step, void *out_overall, uint64_t *act_hist,
+                       uint64_t *bad_rows, StreamArgs &a) {
     if (n_inst < 0) return bad_arg(5, "n_inst < 0");
     if (n_steps < 0) return bad_arg(6, "n_steps < 0");
     if (S <= 0) return bad_arg(7, "S <= 0");
@@ -872,12 +916,32 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
     if (p->rule_act < 0 || p->rule_act >= A) return bad_arg(9, "rule_act outside [0, A)");
     if (p->n_thres < 0) return bad_arg(9, "n_thres < 0");
     if (n_steps > 0x7fffffc0ll) return bad_arg(6, "n_steps does not fit the 32-bit row counters");
+    if ((n_inst + 3) / 4 > 0x7fffffffll) return bad_arg(5, "n_inst too large for one launch");
+    if (n_inst > 0 && !out_activation_step) return bad_arg(13, "out_activation_step is null");
+    a.out_activation = reinterpret_cast<long long *>(out_activation_step);
+    a.out_overall = out_overall;
+    a.act_hist = reinterpret_cast<unsigned long long *>(act_hist);
+    a.bad_rows = reinterpret_cast<unsigned long long *>(bad_rows);
+    a.n_inst = n_inst; a.n_steps = (unsigned)n_steps; a.S = S; a.A = A;
+    a.c_h = p->scale * sqrt(log(1.0 / p->alpha) / 2.0);
+    a.cap = p->cap; a.prior_rule = p->prior_rule; a.prior_other = p->prior_other;
+    a.bonus = p->activation_bonus; a.n_thres = p->n_thres; a.rule_act = p->rule_act;
+    return 0;
+}
+
+extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const void *R, int r_is_f64,
+                                   int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
+                                   const dcarl_params *p, void *out_value, int out_is_f64,
+                                   int32_t *out_act, int64_t *out_activation_step, void *out_overall,
+                                   uint64_t *act_hist, uint64_t *bad_rows, void *ws, size_t ws_bytes,
+                                   int variant, dcarl_stream_t stream) {
+    StreamArgs a;
+    if (int rc = stream_args(n_inst, n_steps, S, A, p, out_activation_step, out_overall, act_hist, bad_rows, a))
+        return rc;
     if (n_inst == 0) return 0;
-    if (!out_activation_step) return bad_arg(13, "out_activation_step is null");
     if (n_steps > 0 && (!idx || !act || !R)) return bad_arg(1, "idx/act/R is null");
     if (n_steps > 0 && (!out_value || !out_act)) return bad_arg(10, "out_value/out_act is null");
     if (variant < 0 || variant > 2) return bad_arg(19, "variant must be 0, 1 or 2");
-    if ((n_inst + 3) / 4 > 0x7fffffffll) return bad_arg(5, "n_inst too large for one launch");
 
     const bool fits = kRowsCtaFixedBytes + rows_warp_bytes(S, A) <= kMaxSmemPerCta;
     bool rows = fits;
@@ -887,21 +951,36 @@ extern "C" int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const
         const size_t need = dcarl_stream_bounds_ws(n_inst, n_steps, S, A);
         if (!ws || ws_bytes < need) return bad_arg(17, "workspace too small (see dcarl_stream_bounds_ws)");
     }
-    StreamArgs a;
     a.idx = idx; a.act = act; a.R = R;
     a.out_value = out_value; a.out_act = out_act;
-    a.out_activation = reinterpret_cast<long long *>(out_activation_step);
-    a.out_overall = out_overall;
-    a.act_hist = reinterpret_cast<unsigned long long *>(act_hist);
-    a.bad_rows = reinterpret_cast<unsigned long long *>(bad_rows);
-    a.n_inst = n_inst; a.n_steps = (unsigned)n_steps; a.S = S; a.A = A;
-    a.c_h = p->scale * sqrt(log(1.0 / p->alpha) / 2.0);
-    a.cap = p->cap; a.prior_rule = p->prior_rule; a.prior_other = p->prior_other;
-    a.bonus = p->activation_bonus; a.n_thres = p->n_thres; a.rule_act = p->rule_act;
     cudaStream_t st = (cudaStream_t)stream;
     if (r_is_f64)
         return out_is_f64 ? dispatch_ov<double, double>(a, rows, ws, st) : dispatch_ov<double, float>(a, rows, ws, st);
     return out_is_f64 ? dispatch_ov<float, double>(a, rows, ws, st) : dispatch_ov<float, float>(a, rows, ws, st);
+}
+
+// Compact wire format: one byte per key.  Same kernel, keys widened at the load and the argmax
+// narrowed at the store; float32 returns in, float32 values out.
+extern "C" int dcarl_stream_bounds_u8(const uint8_t *idx, const uint8_t *act, const float *R,
+                                      int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
+                                      const dcarl_params *p, float *out_value, uint8_t *out_act,
+                                      int64_t *out_activation_step, float *out_overall,
+                                      uint64_t *act_hist, uint64_t *bad_rows, dcarl_stream_t stream) {
+    StreamArgs a;
+    if (int rc = stream_args(n_inst, n_steps, S, A, p, out_activation_step, out_overall, act_hist, bad_rows, a))
+        return rc;
+    if (S > 256) return bad_arg(6, "S > 256 does not fit one-byte keys");
+    if (A > 256) return bad_arg(7, "A > 256 does not fit one-byte keys");
+    if (kRowsCtaFixedBytes + rows_warp_bytes(S, A) > kMaxSmemPerCta)
+        return bad_arg(6, "the S*A table does not fit shared memory (use dcarl_stream_bounds)");
+    if (n_inst == 0) return 0;
+    if (n_steps > 0 && (!idx || !act || !R)) return bad_arg(1, "idx/act/R is null");
+    if (n_steps > 0 && (!out_value || !out_act)) return bad_arg(9, "out_value/out_act is null");
+    a.idx = idx; a.act = act; a.R = R;
+    a.out_value = out_value; a.out_act = out_act;
+    cudaStream_t st = (cudaStream_t)stream;
+    return out_overall ? launch_rows<float, float, uint8_t, true>(a, st)
+                       : launch_rows<float, float, uint8_t, false>(a, st);
 }
 
 #ifdef DCARL_DEBUG_TIMING

@@ -32,17 +32,30 @@ class StreamPlan:
     """Pre-allocated device (and pinned host) buffers for repeated batches of one shape."""
 
     def __init__(self, n_inst, n_steps, S, A, params=None, *, r_dtype=torch.float32,
-                 out_dtype=torch.float32, want_overall=True, want_stats=True, variant=0, device=None):
+                 out_dtype=torch.float32, want_overall=True, want_stats=True, variant=0, device=None,
+                 key_dtype=torch.int32):
+        """key_dtype=torch.uint8 selects the compact wire format (dcarl_stream_bounds_u8): idx / act in
+        and the argmax out are one byte each — 6 + 9 bytes per scenario-step instead of 12 + 12 on the
+        host <-> device link.  It needs S, A <= 256, float32 rows and outputs, and a table that fits
+        shared memory; results are identical to the int32 format."""
         _dev.require_cuda()
         self.n_inst, self.n_steps, self.S, self.A = int(n_inst), int(n_steps), int(S), int(A)
         self.params = params or _abi.Params()
         self.r_dtype, self.out_dtype = r_dtype, out_dtype
         self.want_overall, self.want_stats, self.variant = want_overall, want_stats, int(variant)
+        self.key_dtype = key_dtype
+        if key_dtype not in (torch.int32, torch.uint8):
+            raise ValueError("key_dtype must be torch.int32 or torch.uint8")
+        if key_dtype == torch.uint8:
+            if r_dtype != torch.float32 or out_dtype != torch.float32 or self.variant == 1:
+                raise ValueError("the compact wire format is float32 in / float32 out on the row-parallel kernel")
+            if self.S > 256 or self.A > 256 or not _abi.lib().dcarl_stream_rows_fit(self.S, self.A):
+                raise ValueError("the compact wire format needs S, A <= 256 and an S*A table that fits shared memory")
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         shp = (self.n_inst, self.n_steps)
         e = lambda s, d: torch.empty(s, dtype=d, device=self.device)
         self.value = e(shp, out_dtype)
-        self.act = e(shp, torch.int32)
+        self.act = e(shp, key_dtype)
         self.overall = e(shp, out_dtype) if want_overall else None
         self.activation_step = e((self.n_inst, self.S), torch.int64)
         self.act_hist = torch.zeros(self.A, dtype=torch.int64, device=self.device) if want_stats else None
@@ -57,27 +70,47 @@ class StreamPlan:
         self._streams = None
 
     # -- device path -------------------------------------------------------------------------
-    def run_device(self, idx, act, R, stream=None, check=False):
-        """idx/act int32, R r_dtype: CUDA tensors [n_inst, n_steps].  Asynchronous."""
+    def _launch(self, pi, pa, pr, n_inst, value, act, astep, overall, ws, stream):
+        """One dcarl_stream_bounds[_u8] call on raw pointers (c_void_p) for `n_inst` instances."""
         L = _abi.lib()
-        for t, d in ((idx, torch.int32), (act, torch.int32), (R, self.r_dtype)):
-            if not (t.is_cuda and t.dtype == d and t.is_contiguous() and tuple(t.shape) == (self.n_inst, self.n_steps)):
-                raise ValueError("run_device: expected contiguous CUDA tensors [n_inst, n_steps] of int32/int32/R dtype")
         sh = _dev.stream_handle(stream)
-        if self.want_stats:
-            self.act_hist.zero_()
-        self.bad_rows.zero_()
-        _abi.check(L.dcarl_stream_bounds(
-            _dev.ptr(idx), _dev.ptr(act), _dev.ptr(R), int(self.r_dtype == torch.float64),
-            self.n_inst, self.n_steps, self.S, self.A, self.params,
-            _dev.ptr(self.value), int(self.out_dtype == torch.float64), _dev.ptr(self.act),
-            _dev.ptr(self.activation_step), _dev.ptr(self.overall), _dev.ptr(self.act_hist),
-            _dev.ptr(self.bad_rows), _dev.ptr(self.ws), self._ws_bytes, self.variant, sh))
-        if self.want_stats:
-            _abi.check(L.dcarl_stream_stats(
-                _dev.ptr(self.value), int(self.out_dtype == torch.float64), _dev.ptr(self.overall),
-                _dev.ptr(self.activation_step), _dev.ptr(self.act_hist), self.n_inst, self.n_steps,
-                self.S, self.A, _dev.ptr(self.stats), sh))
+        if self.key_dtype == torch.uint8:
+            _abi.check(L.dcarl_stream_bounds_u8(
+                pi, pa, pr, n_inst, self.n_steps, self.S, self.A, self.params, value, act, astep, overall,
+                _dev.ptr(self.act_hist), _dev.ptr(self.bad_rows), sh))
+        else:
+            _abi.check(L.dcarl_stream_bounds(
+                pi, pa, pr, int(self.r_dtype == torch.float64), n_inst, self.n_steps, self.S, self.A, self.params,
+                value, int(self.out_dtype == torch.float64), act, astep, overall,
+                _dev.ptr(self.act_hist), _dev.ptr(self.bad_rows), ws, self._ws_bytes, self.variant, sh))
+
+    def _stats(self, stream):
+        _abi.check(_abi.lib().dcarl_stream_stats(
+            _dev.ptr(self.value), int(self.out_dtype == torch.float64), _dev.ptr(self.overall),
+            _dev.ptr(self.activation_step), _dev.ptr(self.act_hist), self.n_inst, self.n_steps,
+            self.S, self.A, _dev.ptr(self.stats), _dev.stream_handle(stream)))
+
+    def run_device(self, idx, act, R, stream=None, check=False):
+        """idx/act key_dtype, R r_dtype: CUDA tensors [n_inst, n_steps] on the plan's device.
+        Asynchronous on `stream` (default: the current stream of the plan's device)."""
+        for t, d in ((idx, self.key_dtype), (act, self.key_dtype), (R, self.r_dtype)):
+            if not (t.is_cuda and t.device == self.device and t.dtype == d and t.is_contiguous()
+                    and tuple(t.shape) == (self.n_inst, self.n_steps)):
+                raise ValueError(f"run_device: expected contiguous CUDA tensors [n_inst, n_steps] on {self.device} "
+                                 f"of dtype {self.key_dtype} (idx, act) and {self.r_dtype} (R)")
+        # the C ABI launches on the CURRENT device: make the plan's device current, and issue the
+        # zeroing of the accumulators on the same stream as the kernels that add into them
+        with torch.cuda.device(self.device):
+            st = stream if stream is not None else torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(st):
+                if self.want_stats:
+                    self.act_hist.zero_()
+                self.bad_rows.zero_()
+                self._launch(_dev.ptr(idx), _dev.ptr(act), _dev.ptr(R), self.n_inst, _dev.ptr(self.value),
+                             _dev.ptr(self.act), _dev.ptr(self.activation_step), _dev.ptr(self.overall),
+                             _dev.ptr(self.ws), st)
+                if self.want_stats:
+                    self._stats(st)
         if check:
             self.raise_on_bad_rows()
         return StreamResult(self.value, self.act, self.activation_step, self.overall, self.act_hist, self.stats)
@@ -93,36 +126,36 @@ class StreamPlan:
         if self._pinned is None:
             shp = (self.n_inst, self.n_steps)
             pe = lambda d: torch.empty(shp, dtype=d).pin_memory()
-            self._pinned = dict(idx=pe(torch.int32), act=pe(torch.int32), R=pe(self.r_dtype),
-                                value=pe(self.out_dtype), oact=pe(torch.int32),
+            self._pinned = dict(idx=pe(self.key_dtype), act=pe(self.key_dtype), R=pe(self.r_dtype),
+                                value=pe(self.out_dtype), oact=pe(self.key_dtype),
                                 overall=pe(self.out_dtype) if self.want_overall else None,
                                 astep=torch.empty((self.n_inst, self.S), dtype=torch.int64).pin_memory())
             e = lambda d: torch.empty(shp, dtype=d, device=self.device)
-            self._din = (e(torch.int32), e(torch.int32), e(self.r_dtype))
+            self._din = (e(self.key_dtype), e(self.key_dtype), e(self.r_dtype))
         return self._pinned
 
+    def _key_bytes(self):
+        return 1 if self.key_dtype == torch.uint8 else 4
+
     def h2d_bytes(self):
-        return self.n_inst * self.n_steps * (8 + (8 if self.r_dtype == torch.float64 else 4))
+        return self.n_inst * self.n_steps * (2 * self._key_bytes() + (8 if self.r_dtype == torch.float64 else 4))
 
     def d2h_bytes(self):
         w = 8 if self.out_dtype == torch.float64 else 4
-        return self.n_inst * self.n_steps * (4 + w * (2 if self.want_overall else 1)) + self.n_inst * self.S * 8
+        return (self.n_inst * self.n_steps * (self._key_bytes() + w * (2 if self.want_overall else 1))
+                + self.n_inst * self.S * 8)
 
     def _launch_range(self, lo, hi, stream):
         """Kernel launch for instances [lo, hi) of the plan's own input/output buffers."""
         ns = self.n_steps
+        kb = self._key_bytes()
         rb = 8 if self.r_dtype == torch.float64 else 4
         ob = 8 if self.out_dtype == torch.float64 else 4
         di, da, dr = self._din
         off = lambda t, w: C.c_void_p(t.data_ptr() + lo * ns * w) if t is not None else None
-        _abi.check(_abi.lib().dcarl_stream_bounds(
-            off(di, 4), off(da, 4), off(dr, rb), int(self.r_dtype == torch.float64),
-            hi - lo, ns, self.S, self.A, self.params,
-            off(self.value, ob), int(self.out_dtype == torch.float64), off(self.act, 4),
-            C.c_void_p(self.activation_step.data_ptr() + lo * self.S * 8), off(self.overall, ob),
-            _dev.ptr(self.act_hist), _dev.ptr(self.bad_rows),
-            C.c_void_p(self.ws.data_ptr() + (lo * (self._ws_bytes // max(self.n_inst, 1)))), self._ws_bytes,
-            self.variant, _dev.stream_handle(stream)))
+        self._launch(off(di, kb), off(da, kb), off(dr, rb), hi - lo, off(self.value, ob), off(self.act, kb),
+                     C.c_void_p(self.activation_step.data_ptr() + lo * self.S * 8), off(self.overall, ob),
+                     C.c_void_p(self.ws.data_ptr() + (lo * (self._ws_bytes // max(self.n_inst, 1)))), stream)
 
     def run_pinned(self, chunks=4):
         """Inputs already in the plan's pinned host buffers (``plan.pinned()['idx'|'act'|'R']``).
@@ -130,10 +163,14 @@ class StreamPlan:
         kernel, device->host copy — so the two PCIe directions and the kernel overlap.  Returns the
         pinned buffers after everything has drained."""
         pin = self._pin()
+        with torch.cuda.device(self.device):
+            return self._run_pinned(pin, chunks)
+
+    def _run_pinned(self, pin, chunks):
         if self._streams is None:
             self._streams = tuple(torch.cuda.Stream(device=self.device) for _ in range(3))
         s_in, s_k, s_out = self._streams
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self.device)
         for st in self._streams:
             st.wait_stream(cur)
         chunks = max(1, min(int(chunks), self.n_inst))
@@ -162,10 +199,7 @@ class StreamPlan:
                 for h, d in outs:
                     h[lo:hi].copy_(d[lo:hi], non_blocking=True)
         if self.want_stats:
-            _abi.check(_abi.lib().dcarl_stream_stats(
-                _dev.ptr(self.value), int(self.out_dtype == torch.float64), _dev.ptr(self.overall),
-                _dev.ptr(self.activation_step), _dev.ptr(self.act_hist), self.n_inst, self.n_steps,
-                self.S, self.A, _dev.ptr(self.stats), _dev.stream_handle(s_k)))
+            self._stats(s_k)
         for st in self._streams:
             cur.wait_stream(st)
         cur.synchronize()
@@ -189,24 +223,30 @@ class StreamPlan:
 
 
 def stream_bounds(idx, act, R, S, A, params=None, *, want_overall=True, out_dtype=None, variant=0,
-                  want_stats=False):
+                  want_stats=False, key_dtype=torch.int32):
     """One-shot batched call.  idx/act/R: [n_steps] or [n_inst, n_steps]; numpy (host) or CUDA tensors.
 
     R float32 computes from float32 returns, anything else from float64; out_dtype defaults to
-    float64 unless R is float32.  Raises IndexError when a row's idx/act is out of range."""
+    float64 unless R is float32.  key_dtype=torch.uint8 runs the compact wire format (one-byte keys
+    in, one-byte argmax out; float32 only).  Raises IndexError when a row's idx/act is out of range."""
     _dev.require_cuda()
     on_device = _dev.is_device(R)
     r_dt = _dev.float_dtype_of(R)
     o_dt = out_dtype or (torch.float32 if r_dt == torch.float32 else torch.float64)
     if isinstance(o_dt, np.dtype) or o_dt in (np.float32, np.float64):
         o_dt = torch.float32 if np.dtype(o_dt) == np.float32 else torch.float64
-    di, da, dr = _dev.as_device(idx, torch.int32), _dev.as_device(act, torch.int32), _dev.as_device(R, r_dt)
+    if key_dtype == torch.uint8 and not on_device:
+        for name, k, hi in (("idx", idx, S), ("act", act, A)):     # a one-byte cast must not hide a bad key
+            k = np.asarray(k)
+            if k.size and (k.min() < 0 or k.max() > 255):
+                raise IndexError(f"{name} outside [0, {hi}) (the reference raises IndexError on such a row)")
+    di, da, dr = _dev.as_device(idx, key_dtype), _dev.as_device(act, key_dtype), _dev.as_device(R, r_dt)
     single = di.dim() == 1
     if single:
         di, da, dr = di[None], da[None], dr[None]
     n_inst, n_steps = di.shape
     plan = StreamPlan(n_inst, n_steps, S, A, params, r_dtype=r_dt, out_dtype=o_dt, want_overall=want_overall,
-                      want_stats=want_stats, variant=variant, device=di.device)
+                      want_stats=want_stats, variant=variant, device=di.device, key_dtype=key_dtype)
     res = plan.run_device(di.contiguous(), da.contiguous(), dr.contiguous(), check=True)
     sq = (lambda t: t[0]) if single else (lambda t: t)
     conv = (lambda t: t) if on_device else (lambda t: t.cpu().numpy())

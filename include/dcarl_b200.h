@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DCARL_B200_ABI_VERSION 1
+#define DCARL_B200_ABI_VERSION 2
 
 typedef void *dcarl_stream_t; /* cudaStream_t */
 
@@ -86,8 +86,9 @@ int dcarl_bounds(const void *x, int x_is_f64, const int64_t *seg_offsets, int64_
  *   out_activation_step[i,s] = per-state 1-based step at which argmax first left rule_act, else -1
  *   act_hist[A] (nullable, uint64, ACCUMULATED into) = histogram of out_act over all rows.
  * Rows with idx/act out of range are an input error (the reference raises IndexError): they never
- * index out of bounds, leave the outputs of their instance unspecified, and make *bad_rows
- * (nullable, uint64, accumulated) non-zero; callers must treat *bad_rows != 0 as a failed call.
+ * index out of bounds, leave the outputs of their instance unspecified, and are counted, one per
+ * row, into *bad_rows (nullable, uint64, accumulated); callers must treat *bad_rows != 0 as a
+ * failed call.
  * variant: 0 = default (row-parallel shared-memory kernel when the S*A table fits in shared
  * memory, else the global-memory walker), 1 = force the walker, 2 = force the row-parallel kernel
  * (error if it does not fit).  The walker needs a workspace of dcarl_stream_bounds_ws() bytes;
@@ -102,6 +103,18 @@ int dcarl_stream_bounds(const int32_t *idx, const int32_t *act, const void *R, i
                         int64_t *out_activation_step, void *out_overall,
                         uint64_t *act_hist, uint64_t *bad_rows,
                         void *ws, size_t ws_bytes, int variant, dcarl_stream_t stream);
+
+/* Compact wire format of the same call (ST2:72-105 rows whose keys fit one byte, S <= 256 and
+ * A <= 256): idx and act are uint8, R float32, out_value / out_overall (nullable) float32 and
+ * out_act uint8 — 6 bytes in and 9 bytes out per scenario-step instead of 12 + 12, which is what
+ * a host <-> device link carries in the end-to-end path.  Row-parallel kernel only: the S*A table
+ * must fit shared memory (dcarl_stream_rows_fit).  Results are identical to dcarl_stream_bounds on
+ * the widened keys. */
+int dcarl_stream_bounds_u8(const uint8_t *idx, const uint8_t *act, const float *R,
+                           int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
+                           const dcarl_params *p /* host */, float *out_value, uint8_t *out_act,
+                           int64_t *out_activation_step, float *out_overall,
+                           uint64_t *act_hist, uint64_t *bad_rows, dcarl_stream_t stream);
 
 /* The bound of a cell from caller-held moments, exactly as the stream kernel evaluates it:
  * cell i holds n[i] > 0 samples with sum[i] and sumsq[i]; act[i] == rule_act selects the upper

@@ -110,6 +110,40 @@ def box_moments(buf_state, buf_ret, dist, queries, n_actions):
     return out
 
 
+def box_raw(buf_state, buf_ret, dist, queries, n_actions, threads=1):
+    """Raw moments [Q, n_actions, 3] = (n, sum R, sum R^2) in one pass per query (orc_box_raw).  The
+    buffer may be float32 (the device copy, widened per element) or float64.  `threads` > 1 splits the
+    rows into contiguous chunks (ctypes releases the GIL) and adds the partial moments in chunk order."""
+    bs = np.ascontiguousarray(buf_state)
+    f32 = bs.dtype == np.float32
+    if not f32:
+        bs = _f64(bs)
+    br = np.ascontiguousarray(buf_ret, np.float32 if f32 else np.float64)
+    dist, q = _f64(dist).ravel(), _f64(queries)
+    D = bs.shape[1] - 1
+    q = q.reshape(-1, D)
+    Q, M = q.shape[0], bs.shape[0]
+    t = C.c_float if f32 else C.c_double
+
+    def part(lo, hi):
+        out = np.empty((Q, n_actions, 3))
+        lib().orc_box_raw(_p(bs[lo:hi], t), _p(br[lo:hi], t), C.c_int(int(f32)), C.c_long(hi - lo), C.c_int(D),
+                          _p(dist, C.c_double), _p(q, C.c_double), C.c_int(Q), C.c_int(n_actions), _p(out, C.c_double))
+        return out
+
+    threads = max(1, min(int(threads), max(1, M // 4096)))
+    if threads == 1:
+        return part(0, M)
+    from concurrent.futures import ThreadPoolExecutor
+    edges = [M * i // threads for i in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:
+        outs = list(ex.map(lambda e: part(*e), zip(edges[:-1], edges[1:])))
+    tot = outs[0]
+    for o in outs[1:]:
+        tot = tot + o
+    return tot
+
+
 def box_select(nmv, visited_times_thres=10, min_candidate_visits=5, rule_mean_gate=-0.1,
                confidence_thres=0.5):
     nmv = _f64(nmv)

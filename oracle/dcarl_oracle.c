@@ -264,6 +264,46 @@ int orc_box_moments(const double *buf_state, const double *buf_ret, long M, int 
     return 0;
 }
 
+/* Same box test (RLS:161-163, 195-196) restated for large buffers: ONE pass over the stored rows per
+ * query instead of one per (query, candidate action).  A stored row whose observation box contains
+ * the query's observation matches exactly the candidate actions a with
+ * s_act - dist[D] <= a <= s_act + dist[D] (the action is just the last coordinate of the 21-D point,
+ * RLS:91-93), so the count per (query, action) is identical to orc_box_moments.  The buffer is the
+ * float32 copy the device holds, widened to double per element (buf_is_f32 != 0), or the float64
+ * rows themselves.  Output: raw moments out[q, a, {0,1,2}] = {n, sum R, sum R^2} in double, summed in
+ * row order — counts are exact, the sums are compared with a tolerance (tests/test_oracle.py pins this
+ * function against orc_box_moments). */
+int orc_box_raw(const void *buf_state, const void *buf_ret, int buf_is_f32, long M, int D,
+                const double *dist, const double *queries, int Q, int n_actions, double *out)
+{
+    const int W = D + 1;
+    const float *sf = (const float *)buf_state, *rf = (const float *)buf_ret;
+    const double *sd = (const double *)buf_state, *rd = (const double *)buf_ret;
+    for (long i = 0; i < (long)Q * n_actions * 3; i++) out[i] = 0.0;
+    for (int q = 0; q < Q; q++) {
+        const double *x = queries + (long)q * D;
+        double *o = out + (long)q * n_actions * 3;
+        for (long i = 0; i < M; i++) {
+            int ok = 1;
+            for (int d = 0; d < D && ok; d++) {
+                const double s = buf_is_f32 ? (double)sf[i * W + d] : sd[i * W + d];
+                ok = (s - dist[d] <= x[d]) && (x[d] <= s + dist[d]);
+            }
+            if (!ok) continue;
+            const double sa = buf_is_f32 ? (double)sf[i * W + D] : sd[i * W + D];
+            const double r = buf_is_f32 ? (double)rf[i] : rd[i];
+            const double lo = sa - dist[D], hi = sa + dist[D];
+            if (!(lo == lo) || !(hi == hi)) continue;
+            long a0 = (long)ceil(lo), a1 = (long)floor(hi);
+            if (a0 < 0) a0 = 0;
+            if (a1 > n_actions - 1) a1 = n_actions - 1;
+            for (long a = a0; a <= a1; a++)
+                if (lo <= (double)a && (double)a <= hi) { o[a * 3] += 1.0; o[a * 3 + 1] += r; o[a * 3 + 2] += r * r; }
+        }
+    }
+    return 0;
+}
+
 static double norm_cdf(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
 
 /* RLS.act_test, RLS:120-157, for Q queries; nmv = [Q, n_actions, 3] from above.

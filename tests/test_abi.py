@@ -37,7 +37,7 @@ def test_library_targets_sm_100a_only():
 
 def test_loads_and_reports_version_and_defaults():
     L = _abi.lib()
-    assert L.dcarl_abi_version() == 1
+    assert L.dcarl_abi_version() == _abi.ABI_VERSION == 2
     p = _abi.Params(alpha=0, scale=0, cap=0, prior_rule=0, prior_other=0, activation_bonus=0, n_thres=0, rule_act=5)
     L.dcarl_default_params(C.byref(p))
     assert (p.alpha, p.scale, p.cap, p.prior_rule, p.prior_other, p.activation_bonus, p.n_thres, p.rule_act) == \

@@ -148,6 +148,32 @@ def test_box_golden(golden):
         assert int(buf.act_test(obs)) == picks[qi]
 
 
+def test_box_raw_single_pass_matches_the_per_action_oracle(golden):
+    """orc_box_raw (one pass per query, used for full-size config-4 parity) against orc_box_moments
+    (one pass per (query, action), the literal restatement) and against the reference's own log."""
+    g = golden("rls_box")
+    vs, vv, dr, dist = g["visited_state"], g["visited_value"], g["driving_record"], g["dist"]
+    q = dr[:40, :20]
+    nmv = cport.box_moments(vs, vv[:, 1], dist, q, 8)
+    for threads in (1, 3):
+        raw = cport.box_raw(vs, vv[:, 1], dist, q, 8, threads=threads)
+        assert np.array_equal(raw[:, :, 0], nmv[:, :, 0])                # counts: exact
+        n = np.maximum(raw[:, :, 0], 1)
+        hit = raw[:, :, 0] > 0
+        assert np.abs(raw[:, :, 1] / n - nmv[:, :, 1])[hit].max() < 1e-12
+        assert np.abs(raw[:, :, 2] / n - (raw[:, :, 1] / n) ** 2 - nmv[:, :, 2])[hit].max() < 1e-12
+    assert np.array_equal(cport.box_raw(vs, vv[:, 1], dist, dr[:, :20], 8, threads=2)[:, 0, 0], dr[:, 23])
+    # float32 copy of the buffer (what the device holds), widened per element
+    rng = np.random.default_rng(5)
+    D = 20
+    st = np.hstack([rng.normal(0, 1, (3000, D)) * 0.4 * dist[:D], rng.integers(0, 6, (3000, 1)).astype(float)]).astype(np.float32)
+    rt = (-0.95 ** rng.integers(0, 10, 3000)).astype(np.float32)
+    qs = st[:5, :D].astype(np.float64)
+    a = cport.box_raw(st, rt, dist, qs, 6)
+    b = cport.box_moments(st.astype(np.float64), rt.astype(np.float64), dist, qs, 6)
+    assert np.array_equal(a[:, :, 0], b[:, :, 0]) and a[:, :, 0].sum() > 20
+
+
 def test_box_select_candidate_branch():
     """act_test's a>=1 branch is not exercised by any reference artefact: pin C vs the literal port."""
     rng = np.random.default_rng(11)

@@ -29,7 +29,7 @@ def _sass(symbol_part):
 
 @pytest.fixture(scope="module")
 def rows_sass():
-    return _sass("k_stream_rowsIffLb1ELb0E")        # float rows, float outputs, overall on, priors' argmax = rule
+    return _sass("k_stream_rowsIffiLb1ELb0E")        # float rows, float outputs, overall on, priors' argmax = rule
 
 
 def test_stream_main_loop_is_warp_uniform(rows_sass):
@@ -43,12 +43,15 @@ def test_stream_main_loop_is_warp_uniform(rows_sass):
     assert sum("MATCH.ANY" in s for s in loop) == 2 and sum(s.startswith("LDG") or " LDG" in s for s in loop) == 3
     assert any("REDUX" in s for s in loop)                       # exact top-2 of the replay path
     assert any("MUFU.RSQ64H" in s for s in loop)                 # 1/sqrt seeds of the bound
+    # the cell moments {sum, sum of squares} move as one 16-byte access each way
+    assert any(s.split()[-3:][0].startswith("LDS.128") or "LDS.128" in s for s in loop)
+    assert any("STS.128" in s for s in loop)
 
 
 def test_register_budget_of_the_row_kernel():
     out = subprocess.run(["cuobjdump", "-res-usage", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     rows = re.findall(r"Function (\S*k_stream_rows\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
-    assert len(rows) == 16                                       # RT x OT x overall x force-first
+    assert len(rows) == 20                                       # RT x OT x overall x force-first, + 4 with one-byte keys
     for name, reg, stack in rows:
         assert int(reg) <= 72 and int(stack) == 0, (name, reg, stack)   # 28 warps per SM, nothing spilled
 

@@ -99,6 +99,83 @@ def test_float32_inputs_and_outputs(variant):
     assert no_ov.overall is None and np.array_equal(no_ov.act, res.act) and np.array_equal(no_ov.value, res.value)
 
 
+def test_compact_wire_format_matches_int32_keys():
+    """dcarl_stream_bounds_u8: one-byte keys in, one-byte argmax out — same bits as the int32 format."""
+    for (n_inst, n_steps, S, A, kw) in [(40, 3000, 20, 11, {}), (9, 777, 1, 30, {}), (5, 1200, 3, 200, {"rule_act": 7}),
+                                        (6, 800, 4, 6, {"prior_rule": -80.0})]:
+        idx, act, R = synth_streams(n_inst, n_steps, S, A, seed=31 + S, r_dtype=np.float32)
+        p = _abi.Params(**kw)
+        wide = dc.stream_bounds(idx, act, R, S, A, p, want_stats=True)
+        for ov in (True, False):
+            c = dc.stream_bounds(idx.astype(np.uint8), act.astype(np.uint8), R, S, A, p, key_dtype=torch.uint8,
+                                 want_overall=ov, want_stats=True)
+            assert c.act.dtype == np.uint8 and c.value.dtype == np.float32
+            assert np.array_equal(c.act, wide.act) and np.array_equal(c.value, wide.value)
+            assert np.array_equal(c.activation_step, wide.activation_step)
+            assert np.array_equal(c.act_hist, wide.act_hist)
+            if ov:
+                assert np.array_equal(c.overall, wide.overall)
+    # host path of a plan with one-byte keys: pinned staging carries 6 + 9 bytes per step
+    idx, act, R = synth_streams(64, 2048, 20, 11, seed=8, r_dtype=np.float32)
+    plan = dc.StreamPlan(64, 2048, 20, 11, key_dtype=torch.uint8)
+    assert plan.h2d_bytes() == 64 * 2048 * 6 and plan.d2h_bytes() == 64 * 2048 * 9 + 64 * 20 * 8
+    h = plan.run_host(idx, act, R)
+    ref = dc.stream_bounds(idx, act, R, 20, 11)
+    assert np.array_equal(h.act, ref.act) and np.array_equal(h.value, ref.value) and np.array_equal(h.overall, ref.overall)
+    with pytest.raises(ValueError):
+        dc.StreamPlan(4, 100, 300, 4, key_dtype=torch.uint8)             # S does not fit one byte
+    with pytest.raises(IndexError):
+        dc.stream_bounds(np.full((2, 50), 300), np.zeros((2, 50), np.int64), np.zeros((2, 50), np.float32), 20, 11,
+                         key_dtype=torch.uint8)
+
+
+def test_bad_rows_are_counted_per_row():
+    idx, act, R = synth_streams(3, 500, 4, 5, seed=2, r_dtype=np.float32)
+    idx[0, 7] = 4; act[0, 7] = 9            # one row, both keys bad: still one row
+    idx[1, 33:40] = -1                      # seven rows of one warp batch
+    act[2, 499] = 5                         # the last row of the ragged tail
+    for variant in (0, 1):
+        plan = dc.StreamPlan(3, 500, 4, 5, variant=variant)
+        plan.run_device(*[torch.from_numpy(x).cuda() for x in (idx, act, R)])
+        assert int(plan.bad_rows.item()) == 9
+        with pytest.raises(IndexError, match="9 rows"):
+            plan.raise_on_bad_rows()
+
+
+def test_constant_and_nearly_constant_cells():
+    """A cell whose returns are all equal has sigma == 0 exactly in the reference (two-pass np.std); the
+    kernel's one-pass variance must not turn rounding residue of s2/n - mean^2 into a spurious sigma."""
+    rng = np.random.default_rng(11)
+    n_inst, n_steps, S, A = 8, 1500, 2, 4
+    idx = rng.integers(0, S, (n_inst, n_steps)).astype(np.int32)
+    act = rng.integers(0, A, (n_inst, n_steps)).astype(np.int32)
+    base = np.array([[37.3, 91.7, -12.9, 64.123456789], [1e3 / 7, 55.5, 80.1, 80.1]])   # non-dyadic constants
+    R = base[idx, act]
+    R[:, ::97] += 1e-3                                                   # a few rows make some cells nearly constant
+    for variant in (0, 1):
+        res = dc.stream_bounds(idx, act, R, S, A, _abi.Params(n_thres=3), variant=variant)
+        # nearly constant cells: the one-pass variance resolves sigma only down to ~sqrt(n) 1e-8 |mean|,
+        # which moves the bound by less than 1e-6 (the path's tolerance is 1e-5)
+        compare_stream(res, _oracle(idx, act, R, S, A, n_thres=3), value_tol=1e-6, max_near_ties=2)
+    Rc = base[idx, act]                                                  # exactly constant cells: sigma = 0 exactly
+    for variant in (0, 1):
+        res = dc.stream_bounds(idx, act, Rc, S, A, _abi.Params(n_thres=3), variant=variant)
+        compare_stream(res, _oracle(idx, act, Rc, S, A, n_thres=3), value_tol=1e-11, max_near_ties=2)
+    # exactly constant: the closed form of the bound with sigma = 0
+    n = np.arange(4, 400, dtype=np.int32)
+    c = 64.123456789
+    s1 = np.cumsum(np.full(400, c))[n - 1]
+    s2 = np.cumsum(np.full(400, c * c))[n - 1]
+    out = torch.empty(len(n), dtype=torch.float64, device="cuda")
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", d)
+    _abi.check(_abi.lib().dcarl_cell_values(dc._dev.ptr(t(n, torch.int32)), dc._dev.ptr(t(s1, torch.float64)),
+                                            dc._dev.ptr(t(s2, torch.float64)), dc._dev.ptr(t(np.ones(len(n)), torch.int32)),
+                                            len(n), _abi.Params(), dc._dev.ptr(out), dc._dev.stream_handle()))
+    ch = 150.0 * np.sqrt(np.log(20.0) / 2)
+    want = np.minimum(c - ch / np.sqrt(n), c - ch / np.sqrt(n + 1.0))   # min(lower, CI lower) with sigma = 0
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-11
+
+
 def test_integer_returns_make_exact_ties():
     rng = np.random.default_rng(3)
     n_inst, n_steps, S, A = 16, 1500, 3, 5
