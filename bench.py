@@ -32,6 +32,14 @@ METRIC = "scenario-steps/sec (rollout+confidence)"
 WORKLOAD = "config2: Simulation_2 stream, 4096 instances x 20000 steps, S=20, A=11, f32 rows, overall_value on"
 
 
+def config_dict(n_inst, n_steps, world):
+    """The `config` object both arms print (the reference arm times a bounded sample of this workload)."""
+    return {"workload": WORKLOAD, "n_inst_per_gpu": n_inst, "n_steps": n_steps, "S": S, "A": A,
+            "io": "f32 rows in, f32 value/overall + i32 argmax out; float64 accumulation and bounds",
+            "cache": "inputs (983 MB) + outputs (983 MB) per step exceed the 126 MB L2",
+            "parallelism": f"instances sharded, {world} rank(s), one stats all-reduce per step"}
+
+
 def _cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -187,6 +195,37 @@ def ncu_traffic():
         return None
 
 
+def pcie_probe(dev, nb_in, nb_out, ddist, reps=3):
+    """Bare cudaMemcpyAsync of one step's bytes, both directions at once on two streams, no kernel:
+    the floor of the end-to-end time on this host (max over ranks, all ranks copying at once)."""
+    import torch
+    hin = torch.empty(nb_in, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(nb_out, dtype=torch.uint8).pin_memory()
+    din = torch.empty(nb_in, dtype=torch.uint8, device=dev)
+    dout = torch.zeros(nb_out, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def once():
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+
+    once()
+    ddist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ddist.allreduce_max(t)
+    ms = float(t[0])
+    return {"ms": ms, "h2d_GBs": nb_in / ms / 1e6, "d2h_GBs": nb_out / ms / 1e6,
+            "note": "per rank: pinned-host copies of one step's bytes, both directions concurrently, no kernel"}
+
+
 # ---- this repo's arm ---------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -256,23 +295,37 @@ def run_ours(args):
     stats = plan.stats.cpu().numpy()
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ---------------------
-    pin = plan.pinned()
-    pin["idx"].copy_(idx); pin["act"].copy_(act); pin["R"].copy_(R)
-    torch.cuda.synchronize()
-    e2e_steps = max(2, min(args.steps, 5))
-    plan.run_pinned()                                   # warm-up (first touch of the pinned pages)
-    ddist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        plan.run_pinned()                               # returns after the stream drained
-        ddist.allreduce_stats(plan.stats)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    ddist.allreduce_max(t)
-    e2e_ms = float(t[0])
-    same = bool(torch.equal(pin["value"], plan.value.cpu())) and bool(torch.equal(pin["oact"], plan.act.cpu()))
+    # The public call is StreamPlan.run_pinned.  Headline: the compact wire format (one-byte keys in, one-byte
+    # argmax out: 6 + 9 bytes per scenario-step on the link); the int32 format (12 + 12) is timed beside it.
+    def e2e_leg(key_dtype):
+        ep = dc.StreamPlan(n_inst, n_steps, S, A, r_dtype=torch.float32, out_dtype=torch.float32,
+                           want_overall=True, want_stats=True, key_dtype=key_dtype)
+        pin = ep.pinned()
+        pin["idx"].copy_(idx.to(key_dtype)); pin["act"].copy_(act.to(key_dtype)); pin["R"].copy_(R)
+        torch.cuda.synchronize()
+        k = max(2, min(args.steps, 5))
+        ep.run_pinned()                                   # warm-up (first touch of the pinned pages)
+        ddist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            ep.run_pinned()                               # returns after the stream drained
+            ddist.allreduce_stats(ep.stats)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / k
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        ddist.allreduce_max(t)
+        same = (bool(torch.equal(pin["value"], plan.value.cpu())) and bool(torch.equal(pin["overall"], plan.overall.cpu()))
+                and bool(torch.equal(pin["oact"].to(torch.int32), plan.act.cpu())))
+        res = {"ms_per_step": float(t[0]), "h2d_bytes_per_step": ep.h2d_bytes(), "d2h_bytes_per_step": ep.d2h_bytes(),
+               "outputs_match_device_run": same}
+        del ep, pin
+        torch.cuda.empty_cache()
+        return res
+
+    e2e_c = e2e_leg(torch.uint8)
+    e2e_w = e2e_leg(torch.int32)
+    probe = pcie_probe(dev, e2e_c["h2d_bytes_per_step"], e2e_c["d2h_bytes_per_step"], ddist)
 
     out = None
     if rank == 0:
@@ -281,17 +334,24 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": "scenario-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_inst_per_gpu": n_inst, "n_steps": n_steps, "S": S, "A": A,
-                       "io": "f32 rows in, f32 value/overall + i32 argmax out; float64 accumulation and bounds",
-                       "cache": "inputs (983 MB) + outputs (983 MB) per step exceed the 126 MB L2",
-                       "parallelism": f"instances sharded, {world} rank(s), one stats all-reduce per step"},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "io_dtype": "f32 rows in, f32 values out (the arithmetic type is float64: moments and bounds)",
+        "data": "synthetic",
+            "config": config_dict(n_inst, n_steps, world),
             "clocks": dict(sampler.summary(), sampled_over=clocks_from),
-            "e2e": {"value": total_steps / (e2e_ms * 1e-3), "unit": "scenario-steps/s",
-                    "h2d_bytes_per_step": plan.h2d_bytes(), "d2h_bytes_per_step": plan.d2h_bytes(),
-                    "ms_per_step": e2e_ms, "outputs_match_device_run": same,
-                    "api": "dcarl_b200.StreamPlan.run_pinned (pinned host in/out, copies in the timed region)"},
+            "e2e": {"value": total_steps / (e2e_c["ms_per_step"] * 1e-3), "unit": "scenario-steps/s",
+                    "h2d_bytes_per_step": e2e_c["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e_c["d2h_bytes_per_step"],
+                    "ms_per_step": e2e_c["ms_per_step"], "outputs_match_device_run": e2e_c["outputs_match_device_run"],
+                    "pcie_GBs": {"h2d": e2e_c["h2d_bytes_per_step"] / e2e_c["ms_per_step"] / 1e6,
+                                 "d2h": e2e_c["d2h_bytes_per_step"] / e2e_c["ms_per_step"] / 1e6,
+                                 "note": "per rank, bytes of one step / its end-to-end time; the two directions overlap"},
+                    "wire": "compact: uint8 idx/act + f32 R in, f32 value/overall + uint8 argmax out (6 + 9 B per scenario-step)",
+                    "api": "dcarl_b200.StreamPlan(key_dtype=uint8).run_pinned (pinned host in/out, copies in the timed region)",
+                    "int32_wire": {"value": total_steps / (e2e_w["ms_per_step"] * 1e-3), "ms_per_step": e2e_w["ms_per_step"],
+                                   "h2d_bytes_per_step": e2e_w["h2d_bytes_per_step"],
+                                   "d2h_bytes_per_step": e2e_w["d2h_bytes_per_step"],
+                                   "outputs_match_device_run": e2e_w["outputs_match_device_run"]},
+                    "bare_copy_probe": probe},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "kernel": "k_stream_rows",
@@ -301,10 +361,20 @@ def run_ours(args):
         }
     if rank == 0 and world == 1 and not args.no_cpu:
         out.update(cpu_legs(plan, idx, act, R))
+    # BASELINE configs 4 and 5 at this world size (every rank takes part; rank 0 reports)
+    del idx, act, R
+    plan = None
+    torch.cuda.empty_cache()
+    if not args.no_configs:
+        peak = measured_peak()[0]
+        for name, leg in (("config4", config4_leg), ("config5", config5_leg)):
+            try:
+                res = leg(dev, rank, world, peak, args)
+            except Exception as e:   # noqa: BLE001  (a failing leg must not cost the headline line; every rank fails alike)
+                res = {"error": repr(e)}
+            if rank == 0:
+                out[name] = res
     if rank == 0 and world == 1 and not args.no_secondary:
-        del idx, act, R
-        plan = None
-        torch.cuda.empty_cache()
         try:
             out["secondary"] = secondary(dev, measured_peak()[0])
         except Exception as e:   # noqa: BLE001  (secondary numbers must never cost the headline line)
@@ -317,8 +387,8 @@ def run_ours(args):
 
 
 def secondary(dev, peak):
-    """Roofline of the other kernels on the path (BASELINE configs 3 and 4, single-GPU share):
-    CUDA-event time of back-to-back launches on inputs larger than L2."""
+    """Roofline of the other kernels on the path (BASELINE config 3, planner row f3): CUDA-event time of
+    back-to-back launches on inputs larger than L2.  Configs 4 and 5 have their own legs (every world size)."""
     import torch
     import dcarl_b200 as dc
     out = {}
@@ -334,33 +404,7 @@ def secondary(dev, peak):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    # config 4 (one GPU's view): 1e7-row buffer, 256 candidate actions, Q = 1 and Q = 64
     g = torch.Generator(device=dev).manual_seed(3000)
-    M, NA = 10_000_000, 256
-    dist = torch.tensor(dc.VISITED_STATE_DIST[0], dtype=torch.float64, device=dev)
-    centers = torch.randn((4096, 20), generator=g, device=dev) * dist[:20].float()
-    buf = dc.BoxBuffer(20, capacity=M)
-    st = centers[torch.randint(0, 4096, (M,), generator=g, device=dev)]
-    st += torch.randn((M, 20), generator=g, device=dev) * (0.25 * dist[:20].float())
-    a = torch.randint(0, NA, (M, 1), generator=g, device=dev).float()
-    ret = -(0.95 ** torch.randint(0, 10, (M,), generator=g, device=dev).float()) * (torch.rand(M, generator=g, device=dev) < 0.5)
-    buf.append(torch.cat([st, a], 1), ret)
-    del st, a, ret
-    for Q in (1, 64):
-        q = centers[:Q].double().contiguous()
-        mom = torch.empty((Q, NA, 3), dtype=torch.float64, device=dev)
-        ms = timed(lambda: buf.moments(q, NA, out=mom), 20)
-        gbs = M * 88 / (ms * 1e-3) / 1e9
-        out[f"box_moments_Q{Q}"] = {"rows": M, "n_actions": NA, "ms": ms, "rows_per_s": M / (ms * 1e-3),
-                                    "queries_per_s": Q / (ms * 1e-3), "achieved_GBs": gbs, "frac": gbs / peak,
-                                    "algorithmic_bytes_per_row": 88, "matched_rows": float(mom[:, :, 0].sum())}
-    run = buf.query_graph(1, NA)
-    q1 = centers[:1].double().contiguous()
-    ms = timed(lambda: run(q1), 50)
-    out["box_query_graph_Q1"] = {"rows": M, "ms": ms, "queries_per_s": 1 / (ms * 1e-3), "achieved_GBs": M * 88 / (ms * 1e-3) / 1e9,
-                                 "frac": M * 88 / (ms * 1e-3) / 1e9 / peak,
-                                 "note": "whole act_test query as one CUDA-graph replay: query upload + zero + prepare + scan + select"}
-    del buf, run
     # config 3 mode A: 65 536 episodes x 200 draws, deviates supplied (16 B/row) and on-device Philox (12 B/row)
     n = 65536 * 200
     qs = torch.rand((20, 11), generator=g, device=dev) * 150 - 50
@@ -392,6 +436,175 @@ def secondary(dev, peak):
     del s0, ra, zs, zr, ac
     out["frenet_plan"] = frenet_leg(dev)
     return out
+
+
+# ---- BASELINE config 4: confidence over a 1e7-row {s,a,R} buffer, 256 candidate actions, row-sharded -------
+C4_ROWS, C4_ACTIONS, C4_CHUNKS = 10_000_000, 256, 8
+
+
+def c4_chunk(c, dev):
+    """Rows [c, c+1) * C4_ROWS / 8 of the global buffer: the same bytes whatever the world size."""
+    import torch
+    import dcarl_b200 as dc
+    g = torch.Generator(device=dev).manual_seed(3000)
+    dist = torch.tensor(dc.VISITED_STATE_DIST[0], dtype=torch.float64, device=dev)
+    centers = torch.randn((4096, 20), generator=g, device=dev) * dist[:20].float()
+    g = torch.Generator(device=dev).manual_seed(3100 + c)
+    m = C4_ROWS // C4_CHUNKS
+    st = centers[torch.randint(0, 4096, (m,), generator=g, device=dev)]
+    st += torch.randn((m, 20), generator=g, device=dev) * (0.25 * dist[:20].float())
+    a = torch.randint(0, C4_ACTIONS, (m, 1), generator=g, device=dev).float()
+    ret = -(0.95 ** torch.randint(0, 10, (m,), generator=g, device=dev).float()) * (torch.rand(m, generator=g, device=dev) < 0.5)
+    return centers, torch.cat([st, a], 1), ret
+
+
+def config4_leg(dev, rank, world, peak, args):
+    """Strong scaling: the buffer is row-sharded M/world per rank, the queries are replicated; one query
+    pass = scan of the shard + sum of the raw moments over ranks + act_test pick on every rank.  Checked in
+    the run against the oracle's single-pass restatement on the same rows (host cores)."""
+    import torch
+    import dcarl_b200 as dc
+    from dcarl_b200 import dist as ddist
+    from oracle import cport
+    if C4_CHUNKS % world:
+        return {"skipped": f"world size {world} does not divide the {C4_CHUNKS} buffer chunks"}
+    mine = range(rank * C4_CHUNKS // world, (rank + 1) * C4_CHUNKS // world)
+    buf = dc.BoxBuffer(20, capacity=len(mine) * (C4_ROWS // C4_CHUNKS))
+    for c in mine:
+        centers, st, ret = c4_chunk(c, dev)
+        buf.append(st, ret)
+        del st, ret
+    out = {"rows": C4_ROWS, "rows_per_gpu": len(buf), "n_actions": C4_ACTIONS, "n_gpus": world, "scaling": "strong",
+           "algorithmic_bytes_per_row": 88}
+    q64 = centers[:64].double().contiguous()
+    results = {}
+    for Q in (1, 64):
+        q = q64[:Q].contiguous()
+        run = ddist.ShardedBoxQuery(buf, Q, C4_ACTIONS)
+        reps = 50 if Q == 1 else 10
+        run(q); run(q)
+        ddist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            mom, mv, pick = run(q)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        ddist.allreduce_max(t)
+        ms = float(t[0])
+        gbs = C4_ROWS * 88 / (ms * 1e-3) / 1e9
+        results[Q] = (mom.clone(), pick.clone())
+        out[f"Q{Q}"] = {"ms_per_query_pass": ms, "queries_per_s": Q / (ms * 1e-3), "rows_per_s": C4_ROWS / (ms * 1e-3),
+                        "achieved_GBs": gbs, "frac_of_aggregate_peak": gbs / (peak * world),
+                        "matched_rows": float(mom[:, :, 0].sum()), "path": run.path}
+    # parity: the oracle on this rank's rows, partial moments summed over ranks like the device's
+    cores = max(1, _cores() // world)
+    t0 = time.perf_counter()
+    ref = cport.box_raw(buf.state.cpu().numpy(), buf.ret.cpu().numpy(), dc.VISITED_STATE_DIST[0], q64.cpu().numpy(),
+                        C4_ACTIONS, threads=cores)
+    dt = time.perf_counter() - t0
+    ref_t = torch.from_numpy(ref).to(dev)
+    ddist.allreduce_stats(ref_t)
+    ref = ref_t.cpu().numpy()
+    n = np.maximum(ref[:, :, 0], 1.0)
+    nmv = np.stack([ref[:, :, 0], np.where(ref[:, :, 0] > 0, ref[:, :, 1] / n, -1.0),
+                    np.where(ref[:, :, 0] > 0, np.maximum(ref[:, :, 2] / n - (ref[:, :, 1] / n) ** 2, 0.0), -1.0)], 2)
+    ref_pick = cport.box_select(nmv)
+    mism, sum_err, pick_mism = 0, 0.0, 0
+    for Q in (1, 64):
+        mom, pick = results[Q][0].cpu().numpy(), results[Q][1].cpu().numpy()
+        mism += int((mom[:, :, 0] != ref[:Q, :, 0]).sum())
+        sum_err = max(sum_err, float(np.abs(mom[:, :, 1:] - ref[:Q, :, 1:]).max()))
+        pick_mism += int((pick != ref_pick[:Q]).sum())
+    out["parity"] = {"count_mismatches": mism, "pick_mismatches": pick_mism, "max_abs_sum_error": sum_err,
+                     "bins_checked": 65 * C4_ACTIONS, "rows_checked_per_rank": len(buf),
+                     "oracle": f"oracle/dcarl_oracle.c orc_box_raw on {cores} host threads per rank, {dt:.1f} s"}
+    out["cpu_baseline"] = {"value": len(buf) * 64 / dt, "unit": "row-queries/s", "cores": cores, "kind": "port",
+                           "sample": f"{len(buf)} rows x 64 queries per rank"}
+    return out
+
+
+# ---- BASELINE config 5: mixed Simulation_1 + Simulation_2 batch, 262 144 scenarios x 500 steps, sharded -------
+C5_INST, C5_STEPS, C5_CHUNK = 262144, 500, 4096
+
+
+def config5_leg(dev, rank, world, peak, args):
+    """Strong scaling: even instance ids are Simulation_1-shaped (S=1, A=30, 11 live actions), odd ids
+    Simulation_2-shaped (S=20, A=11); each rank owns a contiguous block of 4096-instance chunks (the same
+    rows whatever the world size), runs its two launches and ONE all-reduce of the merged stats vector."""
+    import torch
+    import dcarl_b200 as dc
+    from dcarl_b200 import dist as ddist
+    from oracle import cport
+    n_chunks = C5_INST // 2 // C5_CHUNK                       # per shape
+    if n_chunks % world:
+        return {"skipped": f"world size {world} does not divide the {n_chunks} chunks per shape"}
+    mine = range(rank * n_chunks // world, (rank + 1) * n_chunks // world)
+    shapes = ((1, 30, 11), (20, 11, None))
+    data, plans = [], []
+    for si, (s_, a_, live) in enumerate(shapes):
+        parts = [synth_device(C5_CHUNK, C5_STEPS, 4000 + 2 * c + si, dev, S=s_, A=a_, live=live) for c in mine]
+        data.append(tuple(torch.cat([p[j] for p in parts]) for j in range(3)))
+        plans.append(dc.StreamPlan(len(mine) * C5_CHUNK, C5_STEPS, s_, a_, want_overall=True, want_stats=True))
+    del parts
+    batch = ddist.MixedStreamBatch(plans, keep_local=False)   # the last summary kernel ends with the sum over ranks
+
+    def step():
+        return batch.run(data)
+
+    for _ in range(3):
+        stats = step()
+    ddist.barrier()
+    torch.cuda.synchronize()
+    reps = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        stats = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    ddist.allreduce_max(t)
+    ms = float(t[0])
+    for pl in plans:
+        pl.raise_on_bad_rows()
+    total = C5_INST * C5_STEPS
+    gbs = total * BYTES_PER_STEP / (ms * 1e-3) / 1e9
+    # parity 1: sampled instances of this rank against the oracle (argmax and activation step bit-exact)
+    rng = np.random.default_rng(77 + rank)
+    mism, rows_checked, act_mism = 0, 0, 0
+    for (s_, a_, _), pl, (i_, a__, r_) in zip(shapes, plans, data):
+        pick = torch.from_numpy(rng.choice(pl.n_inst, 16, replace=False)).to(dev)
+        ref = cport.stream(i_[pick].cpu().numpy(), a__[pick].cpu().numpy(), r_[pick].cpu().numpy().astype(np.float64), s_, a_)
+        mism += int((ref["act"] != pl.act[pick].cpu().numpy()).sum())
+        act_mism += int((ref["activation_step"] != pl.activation_step[pick].cpu().numpy()).sum())
+        rows_checked += 16 * C5_STEPS
+    pm = torch.tensor([mism, act_mism, rows_checked], dtype=torch.float64, device=dev)
+    ddist.allreduce_stats(pm)
+    # parity 2: the all-reduced vector against the rank-ordered sum of the local vectors
+    stats = stats.clone()
+    batch.keep_local = True                                   # one more batch that keeps this rank's own vector
+    stats_unfused = batch.run(data)
+    local = batch.local_stats.clone()
+    gathered = ddist.allgather(local)
+    fixed = torch.stack(gathered).sum(0)
+    st, fx = stats.cpu().numpy(), fixed.cpu().numpy()
+    return {"scenarios": C5_INST, "steps": C5_STEPS, "scenarios_per_gpu": 2 * len(mine) * C5_CHUNK, "n_gpus": world,
+            "scaling": "strong", "ms_per_batch": ms, "value": total / (ms * 1e-3), "unit": "scenario-steps/s",
+            "achieved_GBs": gbs, "frac_of_aggregate_peak": gbs / (peak * world), "algorithmic_bytes_per_step": BYTES_PER_STEP,
+            "timed": "two stream launches + two chained summary kernels, the second ending with the sum over ranks "
+                     "(peer memory), 50 batches back to back",
+            "collective": batch.peers.backend,
+            "parity": {"argmax_mismatches": int(pm[0].item()), "activation_step_mismatches": int(pm[1].item()),
+                       "rows_checked": int(pm[2].item()),
+                       "fused_equals_unfused_collective": bool(torch.equal(stats, stats_unfused)),
+                       "allreduced_vs_rank_ordered_sum": {"integer_fields_equal": bool(np.array_equal(st[2:], fx[2:])),
+                                                          "max_rel_err_float_fields": float(np.abs(st[:2] - fx[:2]).max() / max(1.0, np.abs(fx[:2]).max()))}},
+            "stats": {"sum_final_value": float(st[0]), "sum_final_overall": float(st[1]), "activated_pairs": int(st[2]),
+                      "sum_activation_step": int(st[3]), "total_steps": int(st[4]), "action_histogram": [int(x) for x in st[5:]],
+                      "note": "the integer fields are identical for every world size (same rows, exact sums)"}}
 
 
 def synth_frenet(n, n_paths, seed, max_obs=4):
@@ -506,11 +719,11 @@ def run_reference(args):
     cores = _cores()
     procs = min(cores, 64)
     # ~3.5 s per 20 000-step instance per core: size the per-step sample so K+W steps end in minutes
-    per_core = int(min(4, max(1, 150.0 / (args.steps + 1) / 3.5)))
+    per_core = int(min(4, max(1, 150.0 / (args.steps + max(args.warmup, 3)) / 3.5)))
     n_lit = per_core * procs
     idx, act, R = synth_host(n_lit, args.n_steps, 1000)
-    warm = max(args.warmup, 0)
-    for _ in range(min(warm, 1)):
+    warm = max(args.warmup, 3)                   # same rule as our arm
+    for _ in range(warm):
         cpu_literal(idx, act, R, procs)
     times = []
     for _ in range(args.steps):
@@ -520,14 +733,18 @@ def run_reference(args):
     value = idx.size / (ms * 1e-3)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scenario-steps/s", "n_gpus": world,
-        "steps": args.steps, "warmup": min(warm, 1), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_steps": args.n_steps, "S": S, "A": A,
-                   "note": "the reference is single-process Python/NumPy and cannot travel to the GPU box; this arm "
-                           "times its literal restatement (oracle/pyref.py, pinned bit-exact against the reference's "
-                           "outputs) on all host cores, one instance per task"},
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "io_dtype": "f32 rows in, f32 values out (the arithmetic type is float64: moments and bounds)",
+        "data": "synthetic",
+        "config": config_dict(args.n_inst, args.n_steps, world),
+        "sampled_instances": n_lit,
+        "note": "the reference is single-process Python/NumPy and cannot travel to the GPU box; this arm times its "
+                "literal restatement (oracle/pyref.py, pinned bit-exact against the reference's outputs) on all host "
+                "cores, one instance per task, on a bounded sample of the config's instances per step (rates are per "
+                "scenario-step, so the sample size does not enter the ratio)",
         "cpu_baseline": {"value": value, "unit": "scenario-steps/s", "cores": procs, "kind": "port",
-                         "sample": f"{n_lit} instances x {args.n_steps} steps per step"},
+                         "sample": f"{n_lit} of the {args.n_inst} instances x {args.n_steps} steps per step"},
         "e2e": {"value": value, "unit": "scenario-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -543,7 +760,8 @@ def main():
     ap.add_argument("--n-inst", type=int, default=N_INST, help="instances per GPU (default: config 2)")
     ap.add_argument("--n-steps", type=int, default=N_STEPS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the box / sampler / rollout rooflines")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the sampler / rollout / planner legs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config-4 and config-5 legs")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 3 if args.impl == "reference" else 50

@@ -44,6 +44,15 @@ class RlsParams(C.Structure):
         super().__init__(rule_mean_gate, confidence_thres, visited_times_thres, min_candidate_visits)
 
 
+MAX_PEERS = 16
+
+
+class PeerCtx(C.Structure):
+    """dcarl_peer_ctx — peer-mapped all-reduce workspaces of the ranks of one NVLink box."""
+    _fields_ = [("slots", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS), ("epoch", C.c_void_p),
+                ("rank", C.c_int32), ("world", C.c_int32), ("n_max", C.c_int32), ("pad_", C.c_int32)]
+
+
 FRENET_MAX_D, FRENET_MAX_T, FRENET_MAX_V = 16, 4, 8
 
 
@@ -78,12 +87,21 @@ SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcarl_cell_values": (_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Params), _vp, _vp]),
     "dcarl_stream_stats": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "dcarl_stream_stats_reduce": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _i32, _int,
+                                         C.POINTER(PeerCtx), _vp]),
+    "dcarl_peer_ws_bytes": (_sz, [_i32, _i32]),
+    "dcarl_peer_ws_layout": (None, [_i32, _i32, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "dcarl_peer_allreduce": (_int, [_vp, _i32, C.POINTER(PeerCtx), _vp]),
+    "dcarl_allreduce_stats": (_int, [_vp, _i32, _vp, _vp]),
     "dcarl_sample_returns": (_int, [_vp, _int, _vp, _vp, _int, _vp, _i64, _i32, _i32, _d, _d, _d, _d,
                                     _vp, _vp, _int, _vp]),
     "dcarl_sample_returns_philox": (_int, [_vp, _int, _u64, _i64, _i32, _i32, _d, _d, _d, _d,
                                            _vp, _vp, _vp, _int, _vp]),
     "dcarl_box_moments_ws": (_sz, [_i32, _i32, _i32]),
     "dcarl_box_moments": (_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "dcarl_box_query_ws": (_sz, [_i32, _i32, _i32]),
+    "dcarl_box_query": (_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, C.POINTER(RlsParams), _vp, _vp, _vp,
+                               _vp, _sz, C.POINTER(PeerCtx), _vp]),
     "dcarl_box_select": (_int, [_vp, _i32, _i32, C.POINTER(RlsParams), _vp, _vp, _vp]),
     "dcarl_add_data_counts": (_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dcarl_add_data_rows": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _d, _vp, _vp, _vp]),

@@ -20,6 +20,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace dcarl {
 
@@ -27,14 +28,10 @@ constexpr int kTileRows = 256;
 constexpr int kStages = 4;
 constexpr int kMaxSmemBins = 1024;  // (query, action) bins kept in shared memory: 24 KB
 
-// thresholds layout in the workspace: lo[Q][D], hi[Q][D] (float32)
-__global__ void k_box_prepare(const double *__restrict__ queries, const double *__restrict__ dist, int Q,
-                              int D, float *__restrict__ lo, float *__restrict__ hi) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Q * D) return;
-    const int d = i % D;
-    const double q = queries[i], w = dist[d];
-    float h = -CUDART_INF_F, l = CUDART_INF_F;  // empty interval unless proven otherwise
+// Largest float32 s_hi and smallest float32 s_lo with  fl64(s - w) <= q <= fl64(s + w)  <=>  s_lo <= s <= s_hi
+// (exact float64 predicate, +-1 ulp walk around the rounded candidates); an empty interval for NaN inputs.
+__device__ __forceinline__ void box_thresholds(double q, double w, float &l, float &h) {
+    h = -CUDART_INF_F; l = CUDART_INF_F;
     if (q == q && w == w) {
         // hi: largest float s with (double)s - w <= q
         float c = __double2float_rd(q + w);
@@ -53,6 +50,15 @@ __global__ void k_box_prepare(const double *__restrict__ queries, const double *
         for (int it = 0; it < 4 && !(q <= (double)c + w); ++it) c = nextafterf(c, CUDART_INF_F);
         if (q <= (double)c + w) l = c;
     }
+}
+
+// thresholds layout in the workspace: lo[Q][D], hi[Q][D] (float32)
+__global__ void k_box_prepare(const double *__restrict__ queries, const double *__restrict__ dist, int Q,
+                              int D, float *__restrict__ lo, float *__restrict__ hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q * D) return;
+    float l, h;
+    box_thresholds(queries[i], dist[i % D], l, h);
     lo[i] = l;
     hi[i] = h;
 }
@@ -64,8 +70,16 @@ struct BoxArgs {
     int D, Q, n_actions;
     const float *lo, *hi;
     const double *dist;  // [D+1]; dist[D] is the action tolerance
-    double *out;  // [Q, n_actions, 3]
+    double *out;  // [Q, n_actions, 3]; the accumulator (zero on entry) in the fused query
     int bins_in_smem;
+    // fused query (k_box_moments<.., true>): thresholds in the prologue, reduction + select in the epilogue
+    const double *queries;     // [Q, D]
+    unsigned *ticket;          // CTAs that have flushed their bins; the last one runs the epilogue and resets it
+    double *out_moments;       // [Q, n_actions, 3] totals (summed over ranks when peers.world > 1)
+    double *out_mv;            // [Q, n_actions, 2], nullable
+    int *out_action;           // [Q], nullable
+    dcarl_rls_params rp;
+    PeerCtx peers;
 };
 
 // Adds (1, r, r*r) of every lane with `hit` into bins[bin*3 ..]; lanes hitting the same bin
@@ -91,7 +105,34 @@ __device__ __forceinline__ void warp_accumulate(bool hit, int bin, double r, dou
     (void)SMEM;
 }
 
-template <int DT>
+// moments -> mean/var (+ sentinel) and the act_test pick of one query
+__device__ __forceinline__ void box_select_one(const double *m, int n_actions, const dcarl_rls_params &rp,
+                                               double *out_mv, int *out_action) {
+    auto mean_var = [&](int a, double &n, double &mean, double &var) {
+        n = m[a * 3];
+        if (n > 0.0) {
+            mean = m[a * 3 + 1] / n;
+            var = fmax(m[a * 3 + 2] / n - mean * mean, 0.0);
+        } else { mean = -1.0; var = -1.0; }                                    // RLS.py:169-170
+    };
+    double n0, mean0, var0;
+    mean_var(0, n0, mean0, var0);
+    int pick = 0;
+    for (int a = 0; a < n_actions; ++a) {
+        double n, mean, var;
+        mean_var(a, n, mean, var);
+        if (out_mv) { out_mv[a * 2] = mean; out_mv[a * 2 + 1] = var; }
+        if (a == 0 || pick != 0) continue;
+        if (n0 < (double)rp.visited_times_thres || n < (double)rp.min_candidate_visits || mean0 > rp.rule_mean_gate)
+            continue;                                                          // RLS.py:141
+        const double z = (mean - mean0) / sqrt(var0 / n0 + var / n);         // RLS.py:144-148
+        const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
+        if (cdf > rp.confidence_thres) pick = a;                               // RLS.py:150-154
+    }
+    if (out_action) *out_action = pick;
+}
+
+template <int DT, bool FUSED>
 __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int D = DT > 0 ? DT : p.D;
@@ -115,13 +156,21 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
     off += p.bins_in_smem ? (size_t)nbins * 3 * sizeof(double) : 0;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + off);
 
-    for (int i = tid; i < p.Q * D; i += kTileRows) { slo[i] = p.lo[i]; shi[i] = p.hi[i]; }
-    if (DT >= 4)
+    if (FUSED) {
+        // every CTA derives the thresholds of its queries itself (Q*D of them: trivial next to a tile)
+        for (int i = tid; i < p.Q * D; i += kTileRows) box_thresholds(p.queries[i], p.dist[i % D], slo[i], shi[i]);
+        __syncthreads();
+    } else {
+        for (int i = tid; i < p.Q * D; i += kTileRows) { slo[i] = p.lo[i]; shi[i] = p.hi[i]; }
+    }
+    if (DT >= 4) {
+        if (!FUSED) __syncthreads();
         for (int q = tid; q < p.Q; q += kTileRows) {
-            const float *l = p.lo + (size_t)q * D, *h = p.hi + (size_t)q * D;
+            const float *l = slo + (size_t)q * D, *h = shi + (size_t)q * D;
             shead[2 * q] = make_float4(l[0], h[0], l[1], h[1]);
             shead[2 * q + 1] = make_float4(l[2], h[2], l[3], h[3]);
         }
+    }
     if (p.bins_in_smem)
         for (int i = tid; i < nbins * 3; i += kTileRows) sbins[i] = 0.0;
     if (tid == 0) {
@@ -222,6 +271,29 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
             if (v != 0.0) atomicAdd(p.out + i, v);
         }
     }
+    if (!FUSED) return;
+    // ---- fused epilogue: the last CTA to arrive owns the totals
+    __shared__ unsigned s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    // totals of this GPU -> out_moments; the accumulator and the ticket are left zeroed for the next call
+    for (int i = tid; i < nbins * 3; i += kTileRows) {
+        const double v = __ldcg(p.out + i);
+        p.out[i] = 0.0;
+        p.out_moments[i] = v;
+    }
+    if (tid == 0) *p.ticket = 0u;
+    __syncthreads();
+    if (p.peers.world > 1) peer_allreduce_cta(p.out_moments, p.out_moments, nbins * 3, p.peers);
+    __syncthreads();
+    for (int q = tid; q < p.Q; q += kTileRows)
+        box_select_one(p.out_moments + (size_t)q * p.n_actions * 3, p.n_actions, p.rp,
+                       p.out_mv ? p.out_mv + (size_t)q * p.n_actions * 2 : nullptr,
+                       p.out_action ? p.out_action + q : nullptr);
 }
 
 // moments -> mean/var (+ sentinel) and the act_test pick, one thread per query
@@ -229,29 +301,8 @@ __global__ void k_box_select(const double *__restrict__ mom, int Q, int n_action
                              double *__restrict__ out_mv, int *__restrict__ out_action) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
-    const double *m = mom + (size_t)q * n_actions * 3;
-    auto mean_var = [&](int a, double &n, double &mean, double &var) {
-        n = m[a * 3];
-        if (n > 0.0) {
-            mean = m[a * 3 + 1] / n;
-            var = fmax(m[a * 3 + 2] / n - mean * mean, 0.0);
-        } else { mean = -1.0; var = -1.0; }                                    // RLS.py:169-170
-    };
-    double n0, mean0, var0;
-    mean_var(0, n0, mean0, var0);
-    int pick = 0;
-    for (int a = 0; a < n_actions; ++a) {
-        double n, mean, var;
-        mean_var(a, n, mean, var);
-        if (out_mv) { out_mv[((size_t)q * n_actions + a) * 2] = mean; out_mv[((size_t)q * n_actions + a) * 2 + 1] = var; }
-        if (a == 0 || pick != 0) continue;
-        if (n0 < (double)rp.visited_times_thres || n < (double)rp.min_candidate_visits || mean0 > rp.rule_mean_gate)
-            continue;                                                          // RLS.py:141
-        const double z = (mean - mean0) / sqrt(var0 / n0 + var / n);         // RLS.py:144-148
-        const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
-        if (cdf > rp.confidence_thres) pick = a;                               // RLS.py:150-154
-    }
-    if (out_action) out_action[q] = pick;
+    box_select_one(mom + (size_t)q * n_actions * 3, n_actions, rp,
+                   out_mv ? out_mv + (size_t)q * n_actions * 2 : nullptr, out_action ? out_action + q : nullptr);
 }
 
 static size_t box_smem_bytes(int Q, int D, int n_actions, bool bins_in_smem) {
@@ -319,13 +370,85 @@ extern "C" int dcarl_box_moments(const float *buf_state, const float *buf_ret, i
         long long grid = (long long)sms * per_sm;
         if (grid > n_tiles) grid = n_tiles;
         if (D == 20) {
-            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_box_moments<20><<<(unsigned)grid, kTileRows, smem, st>>>(a);
+            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_box_moments<20, false><<<(unsigned)grid, kTileRows, smem, st>>>(a);
         } else {
-            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_box_moments<0><<<(unsigned)grid, kTileRows, smem, st>>>(a);
+            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_box_moments<0, false><<<(unsigned)grid, kTileRows, smem, st>>>(a);
         }
         DCARL_LAUNCH_CHECK("k_box_moments");
+    }
+    return 0;
+}
+
+extern "C" size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions) {
+    (void)D;
+    if (Q <= 0 || n_actions <= 0) return 0;
+    return (size_t)Q * n_actions * 3 * sizeof(double) + 16;   // accumulator + ticket
+}
+
+extern "C" int dcarl_box_query(const float *buf_state, const float *buf_ret, int64_t M, int32_t D,
+                               const double *dist, const double *queries, int32_t Q, int32_t n_actions,
+                               const dcarl_rls_params *rp, double *out_moments, double *out_mean_var,
+                               int32_t *out_action, void *ws, size_t ws_bytes, const dcarl_peer_ctx *peers,
+                               dcarl_stream_t stream) {
+    if (M < 0) return bad_arg(3, "M < 0");
+    if (D <= 0 || D > 255) return bad_arg(4, "D must be in [1, 255]");
+    if (Q < 0) return bad_arg(7, "Q < 0");
+    if (n_actions <= 0) return bad_arg(8, "n_actions <= 0");
+    if (!rp) return bad_arg(9, "params is null");
+    if (Q == 0) return 0;
+    if (!dist || !queries) return bad_arg(5, "dist/queries is null");
+    if (!out_moments) return bad_arg(10, "out_moments is null");
+    if (M > 0 && (!buf_state || !buf_ret)) return bad_arg(1, "buffer is null");
+    if (((uintptr_t)buf_state & 15) || ((uintptr_t)buf_ret & 15)) return bad_arg(1, "buffer must be 16-byte aligned");
+    if (!ws || ws_bytes < dcarl_box_query_ws(Q, D, n_actions) || ((uintptr_t)ws & 15))
+        return bad_arg(13, "workspace too small or misaligned (see dcarl_box_query_ws)");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *acc = reinterpret_cast<double *>(ws);
+    unsigned *ticket = reinterpret_cast<unsigned *>(acc + (size_t)Q * n_actions * 3);
+
+    const size_t budget = 200 * 1024;
+    int qc = Q;
+    while (qc > 1 && box_smem_bytes(qc, D, n_actions, false) > budget) qc = (qc + 1) / 2;
+    if (box_smem_bytes(qc, D, n_actions, false) > budget) return bad_arg(4, "D too large for the tile ring");
+    PeerCtx pc;
+    {
+        const int nmsg = ((Q < qc) ? Q : qc) * n_actions * 3;
+        if (int rc = make_peer_ctx(peers, nmsg, 15, pc)) return rc;
+    }
+    const int sms = sm_count();
+    const long long n_tiles = (M + kTileRows - 1) / kTileRows;
+    for (int q0 = 0; q0 < Q; q0 += qc) {
+        const int qn = (Q - q0 < qc) ? Q - q0 : qc;
+        BoxArgs a;
+        a.buf_state = buf_state; a.buf_ret = buf_ret; a.M = M; a.D = D; a.Q = qn; a.n_actions = n_actions;
+        a.lo = nullptr; a.hi = nullptr; a.dist = dist;
+        a.out = acc + (size_t)q0 * n_actions * 3;
+        a.bins_in_smem = (qn * n_actions <= kMaxSmemBins) &&
+                         box_smem_bytes(qn, D, n_actions, true) <= budget;
+        a.queries = queries + (size_t)q0 * D;
+        a.ticket = ticket;
+        a.out_moments = out_moments + (size_t)q0 * n_actions * 3;
+        a.out_mv = out_mean_var ? out_mean_var + (size_t)q0 * n_actions * 2 : nullptr;
+        a.out_action = out_action ? out_action + q0 : nullptr;
+        a.rp = *rp;
+        a.peers = pc;
+        const size_t smem = box_smem_bytes(qn, D, n_actions, a.bins_in_smem);
+        int per_sm = (int)((size_t)(220 * 1024) / smem);
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        long long grid = (long long)sms * per_sm;
+        if (grid > n_tiles) grid = n_tiles;
+        if (grid < 1) grid = 1;                                   // an empty shard still takes part in the reduction
+        if (D == 20) {
+            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_box_moments<20, true><<<(unsigned)grid, kTileRows, smem, st>>>(a);
+        } else {
+            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_box_moments<0, true><<<(unsigned)grid, kTileRows, smem, st>>>(a);
+        }
+        DCARL_LAUNCH_CHECK("k_box_moments (fused query)");
     }
     return 0;
 }

@@ -79,6 +79,22 @@ __device__ __forceinline__ void st_stream(double *p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// Shared-memory accesses by 32-bit shared-space address (no generic-pointer window arithmetic).
+__device__ __forceinline__ void lds_v2f64(unsigned a, double &x, double &y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
 __device__ __forceinline__ double shfl_f64(double v, int src) {
     return __shfl_sync(FULL_MASK, v, src);
 }

@@ -27,6 +27,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace dcarl {
 
@@ -59,46 +60,56 @@ __device__ __forceinline__ double u32_to_double(unsigned n) {
 __device__ __forceinline__ double rsqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;
-    const double e = fma(-t, y, 1.0);
-    const double q = fma(e, 0.375, 0.5);
-    return fma(y * e, q, y);
+    const double t = __dmul_rn(x, y);
+    const double e = __fma_rn(-t, y, 1.0);
+    const double q = __fma_rn(e, 0.375, 0.5);
+    return __fma_rn(__dmul_rn(y, e), q, y);
 }
 
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
 
-// Value of a cell holding n samples with sum s1 and sum of squares s2, given
-// rs = 1/sqrt(n), rs1 = 1/sqrt(n+1) and dn50 = n * 2^-50.
+// Everything the bound needs from the sample count alone: 1/n and c_h/sqrt(n), c_h = scale*sqrt(ln(1/alpha)/2).
+// The row kernel keeps a table of these per CTA (n below the table size: two 16-byte loads replace two
+// 1/sqrt evaluations); every other path builds them on the fly with the same roundings.
+struct __align__(16) NEntry {
+    double inv_n, hn;
+};
+__device__ __forceinline__ NEntry make_entry(double dn, double c_h) {
+    const double rs = rsqrt_pos(dn);
+    NEntry e;
+    e.inv_n = __dmul_rn(rs, rs);
+    e.hn = __dmul_rn(c_h, rs);
+    return e;
+}
+
+// Value of a cell holding n samples with sum s1 and sum of squares s2; e0 / e1 = entries of n / n+1.
 //   rule action:  min(cap, mean + scale*sqrt(L/2/n))                       ST1:12
 //   other:        min(mean - scale*sqrt(L/2/n),                            ST1:16
 //                     sum/n/(n+1) - 4*std/(n+1) + sum/(n+1) - scale*sqrt(L/2/(n+1)))   ST1:24
-// evaluated in float64 (a few ulp from the reference's divide/sqrt chain, far inside
-// the 1e-5 value tolerance; the argmax only flips on ties closer than ~1e-11).
-// The variance comes from one-pass moments, s2/n - mean^2, whose rounding error is bounded by
-// (3n + 4) 2^-53 mean^2: anything at or below 8n 2^-53 mean^2 is indistinguishable from a constant
-// cell and gives sigma = 0 exactly, like the reference's two-pass np.std on constant samples.
-__device__ __forceinline__ double cell_value_rs(double rs, double rs1, double dn50, double s1, double s2,
-                                                bool is_rule, double c_h, double cap) {
-    const double inv_n = rs * rs;
-    const double mean = s1 * inv_n;
-    // +c_h for the rule action (upper bound), -c_h otherwise (lower bound): one fma serves both
-    const double c_s = __hiloint2double(__double2hiint(c_h) ^ (is_rule ? 0 : (int)0x80000000), __double2loint(c_h));
-    const double x = fma(rs, c_s, mean);
-    const double inv_n1 = rs1 * rs1;
-    const double hn1 = c_h * rs1;
-    const double t = mean * mean;
-    const double var = fma(s2, inv_n, -t);
-    const double sigma = var > t * dn50 ? var * rsqrt_pos(var) : 0.0;
-    const double ci = fma(fma(-4.0, sigma, mean) + s1, inv_n1, -hn1);
+// evaluated in float64 with explicit roundings (identical bits on every path; a few ulp from the
+// reference's divide/sqrt chain, far inside the 1e-5 value tolerance; the argmax only flips on ties
+// closer than ~1e-11).  The variance comes from one-pass moments, s2/n - mean^2, whose rounding error is
+// bounded by (3n + 4) 2^-53 mean^2: anything at or below 8n 2^-53 mean^2 is indistinguishable from a
+// constant cell and gives sigma = 0 exactly, like the reference's two-pass np.std on constant samples.
+__device__ __forceinline__ double cell_value_e(const NEntry e0, const NEntry e1, double dn, double s1, double s2,
+                                               bool is_rule, double cap) {
+    const double mean = __dmul_rn(s1, e0.inv_n);
+    // +hn for the rule action (upper bound), -hn otherwise (lower bound)
+    const double hs = __hiloint2double(__double2hiint(e0.hn) ^ (is_rule ? 0 : (int)0x80000000), __double2loint(e0.hn));
+    const double x = __dadd_rn(mean, hs);
+    const double t = __dmul_rn(mean, mean);
+    const double var = __fma_rn(s2, e0.inv_n, -t);
+    // var <= t * n * 2^-50  <=>  var - (t * 2^-50) * n <= 0
+    const double sigma = __fma_rn(-__dmul_rn(t, 8.8817841970012523e-16 /* 2^-50 */), dn, var) > 0.0
+                             ? __dmul_rn(var, rsqrt_pos(var)) : 0.0;
+    const double ci = __fma_rn(__dadd_rn(__fma_rn(-4.0, sigma, mean), s1), e1.inv_n, -e1.hn);
     return dmin(x, is_rule ? cap : ci);
 }
 
 __device__ __forceinline__ double cell_value(unsigned n, double s1, double s2, bool is_rule, double c_h,
                                              double cap) {
     const double dn = u32_to_double(n);
-    // n * 2^-50, exact: the same bit trick with the exponent lowered by 50
-    const double dn50 = __hiloint2double(0x43300000 - (50 << 20), (int)n) - 4.0;
-    return cell_value_rs(rsqrt_pos(dn), rsqrt_pos(dn + 1.0), dn50, s1, s2, is_rule, c_h, cap);
+    return cell_value_e(make_entry(dn, c_h), make_entry(__dadd_rn(dn, 1.0), c_h), dn, s1, s2, is_rule, cap);
 }
 
 // Runner-up bound kept per state: any value in [second, max) keeps both fast-path tests
@@ -207,47 +218,42 @@ __device__ __forceinline__ double scan_step(double x, int off) {
     return r;
 }
 
-// Per-instance tables of the row kernel (shared memory).  Every record is laid out for the widest
-// access the access pattern allows: random gathers by 32 lanes cost one wavefront per conflicting
-// bank group, and 16-byte accesses (8 lanes per wavefront) lose the least to such conflicts — the
-// kernel's first limiter is the shared-memory data pipe (profiles/).
-struct __align__(16) Mom2 {
-    double s1, s2;   // running sum and sum of squares of the cell's returns
+// Per-instance tables of the row kernel (shared memory).  The kernel is bound by issue slots first (time
+// follows the instruction count, profiles/r02_stream_rows_*), by the shared-memory data pipe second: a
+// cell's {s1, s2, val} share one address computation, the counts sit in their own array (a 4-byte field
+// inside a wide record costs far more bank conflicts than it saves instructions: measured).
+struct Cell {
+    double s1, s2;   // running sum and sum of squares of the cell's returns   (moment stage)
+    double val;      // the cell's current bound value                          (selector stage)
 };
 // Per-state record: one 16-byte load per row.  The low 16 mantissa bits of `sub2` carry the state's
 // argmax (15 bits) and its "activated" flag (bit 15), see pack_bound().
 struct __align__(16) StateHot {
     double smax;   // current max_a value[s][a]
-    double sub2;   // runner-up bound: second-best <= sub2 (and < smax unless the top two are closer than ~1e-11)
+    double sub2;   // runner-up bound: second-best <= sub2 (and < smax unless the top two are closer than ~1e-10)
 };
 
 constexpr unsigned kArgMask = 0x7fffu, kActivatedBit = 0x8000u;
 
 // A bound >= b whose low 16 mantissa bits are `payload`.  Any value >= the true second-best keeps
 // the selector's fast path sound (a looser bound only sends more rows to the exact path), so the
-// bound is moved up by less than 2^17 ulp to make room.
+// bound is first moved up by 2^18 ulp, then its low 16 bits are replaced (a change below 2^16 ulp).
 __device__ __forceinline__ double pack_bound(double b, unsigned payload) {
-    long long bits = __double_as_longlong(b);
-    const bool neg = bits < 0;
-    unsigned long long mag = (unsigned long long)bits & 0x7fffffffffffffffull;
-    if (neg) {
-        // towards zero: drop the low bits and one more unit, so that adding the payload stays above b
-        if (mag > 0x7fefffffffffffffull) mag = 0x7fefffffffffffffull;     // -inf (a single action): -DBL_MAX
-        const unsigned long long hi = mag >> 16;
-        if (hi == 0) return __longlong_as_double((long long)payload);     // within 2^-1022 of zero: a tiny positive
-        mag = ((hi - 1) << 16) | payload;
-        return __longlong_as_double((long long)(mag | 0x8000000000000000ull));
-    }
-    unsigned long long hi = (mag >> 16) + 1;                               // away from zero
-    if (hi > (0x7fefffffffffffffull >> 16)) hi = 0x7fefffffffffffffull >> 16;
-    return __longlong_as_double((long long)((hi << 16) | payload));
+    b = b > -1e300 ? b : -1e300;                                   // -inf (a single action) -> finite
+    b = __dadd_rn(__fma_rn(fabs(b), 5.8207660913467407e-11 /* 2^-34 */, b), 1e-300);   // (+1e-300: zeros and denormals)
+    return __hiloint2double(__double2hiint(b), (int)(((unsigned)__double2loint(b) & 0xffff0000u) | payload));
+}
+// Same for a bound known to be finite (every path but the initial one, where a single action gives -inf).
+__device__ __forceinline__ double pack_bound_finite(double b, unsigned payload) {
+    b = __fma_rn(fabs(b), 5.8207660913467407e-11 /* 2^-34 */, b);   // b == 0 stays 0: the payload alone is a tiny positive
+    return __hiloint2double(__double2hiint(b), (int)(((unsigned)__double2loint(b) & 0xffff0000u) | payload));
 }
 __device__ __forceinline__ unsigned bound_payload(double sub2) { return (unsigned)__double2loint(sub2) & 0xffffu; }
 
 __host__ __device__ inline size_t rows_warp_bytes(int S, int A) {
     const size_t ncell = (size_t)S * A;
     size_t b = (size_t)S * (sizeof(StateHot) + 2 * sizeof(int))                    // hot, actstep, flushpt
-               + ncell * (sizeof(Mom2) + sizeof(double) + sizeof(unsigned))        // moments, val, cnt
+               + ncell * (sizeof(Cell) + sizeof(unsigned))                         // cells, cnt
                + (size_t)A * sizeof(unsigned);                                     // per-warp action histogram
     return (b + 15) & ~(size_t)15;
 }
@@ -288,27 +294,29 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     // is warp-uniform, so the warp-synchronous intrinsics below need no divergence fallbacks
     const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
 
+    // One instance per warp.  (A persistent loop over instances was tried: wrapping the batch loop in an
+    // outer loop makes ptxas give up its proof that the warp is converged at the warp-synchronous
+    // intrinsics, and every one of them gets a divergence fallback again — 64 BRA.DIV instead of 0.)
     const long long inst = (long long)blockIdx.x * warps_per_cta + warp;
     if (inst >= p.n_inst) return;
 
     const int S = p.S, A = p.A, ncell = S * A;
     StateHot *hot = reinterpret_cast<StateHot *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
-    Mom2 *mom2 = reinterpret_cast<Mom2 *>(hot + S);
-    double *val = reinterpret_cast<double *>(mom2 + ncell);
-    unsigned *cnt = reinterpret_cast<unsigned *>(val + ncell);
+    Cell *cells = reinterpret_cast<Cell *>(hot + S);
+    unsigned *cnt = reinterpret_cast<unsigned *>(cells + ncell);
     int *actstep = reinterpret_cast<int *>(cnt + ncell);       // activation step per state, -1 = not yet (ST1:58)
     int *flushpt = actstep + S;
     unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
 
     for (int c = lane; c < ncell; c += 32) {
-        mom2[c].s1 = 0.0; mom2[c].s2 = 0.0; cnt[c] = 0u;
-        val[c] = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
+        cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
+        cells[c].val = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
     }
     for (int a = lane; a < A; a += 32) hist[a] = 0u;
     __syncwarp();
     {
         double m0, sec0; int g0;
-        warp_top2(val, 1, A, m0, g0, sec0);
+        warp_top2(&cells[0].val, 3, A, m0, g0, sec0);
         StateHot h0;
         h0.smax = m0; h0.sub2 = pack_bound(runner_up_bound(sec0, m0), (unsigned)g0);
         for (int s = lane; s < S; s += 32) { hot[s] = h0; actstep[s] = -1; flushpt[s] = 0; }
@@ -324,6 +332,9 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         g_rows_timing[inst * 4 + 0] = t; g_rows_timing[inst * 4 + 2] = smid; g_rows_timing[inst * 4 + 3] = wid;
     }
 #endif
+    // the per-state records are addressed by 32-bit shared-space address in the loop: the generic
+    // pointer costs four instructions per batch to rebuild its shared window base
+    const unsigned hot_sa = (unsigned)__cvta_generic_to_shared(hot);
     const unsigned bit = 1u << lane;
     const unsigned lt = bit - 1u, le = lt | bit, gt = ~le;
     auto gt_of = [](int l) { return ~((2u << l) - 1u); };   // lanes strictly above lane l
@@ -342,7 +353,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     const unsigned ebase = (unsigned)inst * n_steps + lane;
 
     double total = 0.0;   // running overall_value (ST2:99-105), warp-uniform
-    unsigned nbad = 0;    // rows of this lane whose key was out of range
+    unsigned clamped = 0;   // lane-local OR of (raw key ^ clamped key): non-zero once a row was out of range
 
     int n_idx = 0, n_act = 0;
     RT n_R = RT(0);
@@ -374,11 +385,11 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     auto p1a_issue = [&](auto tail_tag, const unsigned k, Rows &r, Mom &m) {
         constexpr bool TAIL = decltype(tail_tag)::value;
         const bool in_stream = TAIL ? (k < n_steps) : true;
-        // out-of-range keys are clamped (memory safety) and counted: the call then reports bad rows
-        // (lanes past the end of the stream re-read keys that were already counted)
+        // out-of-range keys are clamped (memory safety) and remembered: such rows are counted at the end
+        // (lanes past the end of the stream re-read keys that were already checked)
         const int s_in = (int)min((unsigned)n_idx, (unsigned)(S - 1));
         const int a = (int)min((unsigned)n_act, (unsigned)(A - 1));
-        if (in_stream && ((n_idx != s_in) | (n_act != a))) ++nbad;
+        clamped |= (unsigned)(n_idx ^ s_in) | (unsigned)(n_act ^ a);
         m.rin = n_R;
         const unsigned e = ebase + (k - lane);
         if (k + 32 < n_steps) { n_idx = (int)ld_stream(gidx + e + 32); n_act = (int)ld_stream(gact + e + 32); n_R = ld_stream(gR + e + 32); }
@@ -388,8 +399,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         r.a = a;
         r.kx = in_stream ? s_in * A + a : 0;
         peer_masks(r.s, a, r.ms, r.mk);   // mk = action peers until p1a_peers
-        const Mom2 mm = mom2[r.kx];        // one 16-byte gather
-        m.acc1 = mm.s1; m.acc2 = mm.s2;
+        const Cell *cell = cells + r.kx;
+        m.acc1 = cell->s1; m.acc2 = cell->s2;
         r.n = cnt[r.kx];
     };
     // peers part: the cell mask, the row's sample count, the return of the oldest in-batch peer
@@ -417,9 +428,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         m.acc2 = fma(x, x, m.acc2);
         __syncwarp();   // every lane has read its cell
         if (r.active && (r.mk & gt) == 0) {
-            Mom2 mm;
-            mm.s1 = m.acc1; mm.s2 = m.acc2;
-            cnt[r.kx] = r.n; mom2[r.kx] = mm;   // one 16-byte scatter
+            Cell *cell = cells + r.kx;
+            cnt[r.kx] = r.n; cell->s1 = m.acc1; cell->s2 = m.acc2;
         }
         r.v = cell_value(r.n, m.acc1, m.acc2, r.a == rule, c_h, cap);
     };
@@ -427,8 +437,9 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
     // ---- selector stage: per-row (max, argmax) of the row's state
     auto p2 = [&](const Rows &r, Sel &o) {
         const int lane_ = lane;
-        StateHot *sh = hot + r.sx;
-        StateHot h = *sh;
+        const unsigned sh_a = hot_sa + (unsigned)r.sx * (unsigned)sizeof(StateHot);
+        StateHot h;
+        lds_v2f64(sh_a, h.smax, h.sub2);
         const bool upd = r.active && r.n > n_thres;                               // ST1:86
         const double v = r.v;
         const int a = r.a;
@@ -483,13 +494,12 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 o.mprev_out = done ? m_prev : o.mprev_out;
                 o.act_prev = done ? activated : o.act_prev;
             }
-            if (done & upd & ((mk & fin & gt) == 0)) val[r.kx] = v;
-            // the state's max only moves when one of its finalized rows is on the argmax cell
+            if (done & upd & ((mk & fin & gt) == 0)) cells[r.kx].val = v;
             const bool last_of_state = done & ((ms & fin & gt) == 0);
-            if (last_of_state & ((tm & ms & fin) != 0)) sh->smax = m_k;
+            if (last_of_state) sts_f64(sh_a, m_k);
             if (lm != 0) {     // rare: the last finalized row of a lifted state re-centres its bound
                 if (last_of_state & ((lm & ms & fin) != 0))
-                    sh->sub2 = pack_bound(runner_up_bound((lifter & (v > B)) ? v : B, m_k), pl);
+                    sts_f64(sh_a + 8u, pack_bound_finite(runner_up_bound((lifter & (v > B)) ? v : B, m_k), pl));
             }
         };
         round(std::true_type{});
@@ -500,14 +510,14 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 __syncwarp();
                 const int sj = __shfl_sync(FULL_MASK, r.s, j);
                 const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
-                if (lane_ == j && upd) val[r.kx] = v;
+                if (lane_ == j && upd) cells[r.kx].val = v;
                 __syncwarp();
-                const unsigned opl = bound_payload(hot[sj].sub2);
+                const unsigned opl = bound_payload(lds_f64(hot_sa + (unsigned)sj * (unsigned)sizeof(StateHot) + 8u));
                 const int o_arg = (int)(opl & kArgMask);
                 const bool o_activated = (opl & kActivatedBit) != 0;
                 double mx, second; int arg;
-                if (A <= 32) warp_top2_small(val + sj * A, 1, A, mx, arg, second);
-                else warp_top2(val + sj * A, 1, A, mx, arg, second);
+                if (A <= 32) warp_top2_small(&cells[sj * A].val, 3, A, mx, arg, second);
+                else warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
                 __syncwarp();   // every lane has read the state record and the values before lane j rewrites them
                 // The argmax only ever changes here, so a state can only activate here (ST1:98-99):
                 // between two exact rows "argmax != rule" implies "already activated".
@@ -528,17 +538,14 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 }
                 if (lane_ == j) {
                     o.g_out = arg; o.m_out = mx; o.mprev_out = m_prev; o.act_prev = o_activated;
-                    StateHot nh;
-                    nh.smax = mx;
-                    nh.sub2 = pack_bound(runner_up_bound(second, mx),
-                                         (unsigned)arg | ((o_activated | activates) ? kActivatedBit : 0u));
-                    *sh = nh;
+                    sts_v2f64(sh_a, mx, pack_bound(runner_up_bound(second, mx),
+                                                   (unsigned)arg | ((o_activated | activates) ? kActivatedBit : 0u)));
                 }
                 __syncwarp();
                 pend &= ~(fin | (1u << j));
                 mine = mine && lane_ > j;
                 if (pend == 0) break;
-                h = *sh;
+                lds_v2f64(sh_a, h.smax, h.sub2);
                 round(std::false_type{});
                 if (fm == 0) break;
             }
@@ -639,9 +646,15 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         for (int a = lane; a < A; a += 32)
             if (hist[a]) atomicAdd(p.act_hist + a, (unsigned long long)hist[a]);
     }
-    if (p.bad_rows != nullptr) {
-        const unsigned tot_bad = __reduce_add_sync(FULL_MASK, nbad);
-        if (lane == 0 && tot_bad) atomicAdd(p.bad_rows, (unsigned long long)tot_bad);
+    if (p.bad_rows != nullptr && __any_sync(FULL_MASK, clamped != 0)) {
+        // cold path: some key of this instance was out of range — count the offending rows exactly
+        unsigned nbad = 0;
+        for (unsigned q = lane; q < n_steps; q += 32) {
+            const unsigned e = (unsigned)inst * n_steps + q;
+            nbad += ((unsigned)gidx[e] >= (unsigned)S) | ((unsigned)gact[e] >= (unsigned)A);
+        }
+        nbad = __reduce_add_sync(FULL_MASK, nbad);
+        if (lane == 0 && nbad) atomicAdd(p.bad_rows, (unsigned long long)nbad);
     }
 }
 
@@ -759,7 +772,8 @@ __global__ void __launch_bounds__(1024) k_stream_stats(const OT *__restrict__ ou
                                                         const long long *__restrict__ activation,
                                                         const unsigned long long *__restrict__ act_hist,
                                                         long long n_inst, long long n_steps, int S, int A,
-                                                        double *__restrict__ stats) {
+                                                        double *stats, int width, int accumulate,
+                                                        const PeerCtx peers) {
     __shared__ double sh[4][1024];
     const int t = threadIdx.x;
     double v = 0.0, o = 0.0, na = 0.0, sa = 0.0;
@@ -794,9 +808,18 @@ __global__ void __launch_bounds__(1024) k_stream_stats(const OT *__restrict__ ou
             for (int q = 0; q < 4; ++q) sh[q][t] += sh[q][t + w];
         __syncthreads();
     }
-    if (t < 4) stats[t] = sh[t][0];
-    if (t == 4) stats[4] = (double)n_inst * (double)n_steps;
-    for (int a = t; a < A; a += 1024) stats[DCARL_STATS_HEADER + a] = act_hist ? (double)act_hist[a] : 0.0;
+    // this call's vector, zero-padded to `width`, optionally on top of what `stats` holds (mixed batches)
+    for (int i = t; i < width; i += 1024) {
+        double x = 0.0;
+        if (i < 4) x = sh[i][0];
+        else if (i == 4) x = (double)n_inst * (double)n_steps;
+        else if (i - DCARL_STATS_HEADER < A) x = act_hist ? (double)act_hist[i - DCARL_STATS_HEADER] : 0.0;
+        stats[i] = accumulate ? stats[i] + x : x;
+    }
+    if (peers.world > 1) {          // one kernel: local reduction, then the sum over ranks through peer memory
+        __syncthreads();
+        peer_allreduce_cta(stats, stats, width, peers);
+    }
 }
 
 // ---- the closed form on caller-held moments (also the precision probe of cell_value) ---------
@@ -839,7 +862,8 @@ static bool priors_argmax_is_rule(const StreamArgs &a) {
 template <typename RT, typename OT, typename KT, bool OV, bool FF>
 static int launch_rows_ff(const StreamArgs &a, cudaStream_t st) {
     const size_t wb = rows_warp_bytes(a.S, a.A);
-    const int wpc = pick_warps_per_cta(a.n_inst, wb, sm_count());
+    const int sms = sm_count();
+    const int wpc = pick_warps_per_cta(a.n_inst, wb, sms);
     const size_t smem = kRowsCtaFixedBytes + wb * wpc;
     auto kern = k_stream_rows<RT, OT, KT, OV, FF>;
     // per launch, not cached: the attribute belongs to the current device's context
@@ -1006,24 +1030,36 @@ extern "C" int dcarl_cell_values(const int32_t *n, const double *sum, const doub
     return 0;
 }
 
-extern "C" int dcarl_stream_stats(const void *out_value, int out_is_f64, const void *out_overall,
-                                  const int64_t *out_activation_step, const uint64_t *act_hist,
-                                  int64_t n_inst, int64_t n_steps, int32_t S, int32_t A, double *stats,
-                                  dcarl_stream_t stream) {
+extern "C" int dcarl_stream_stats_reduce(const void *out_value, int out_is_f64, const void *out_overall,
+                                         const int64_t *out_activation_step, const uint64_t *act_hist,
+                                         int64_t n_inst, int64_t n_steps, int32_t S, int32_t A, double *stats,
+                                         int32_t stats_width, int accumulate, const dcarl_peer_ctx *peers,
+                                         dcarl_stream_t stream) {
     if (n_inst < 0 || n_steps < 0) return bad_arg(6, "negative size");
     if (S <= 0 || A <= 0) return bad_arg(8, "S/A <= 0");
     if (!stats) return bad_arg(10, "stats is null");
+    if (stats_width < DCARL_STATS_HEADER + A) return bad_arg(11, "stats_width < DCARL_STATS_HEADER + A");
     if (n_inst > 0 && !out_activation_step) return bad_arg(4, "out_activation_step is null");
     if (n_inst > 0 && n_steps > 0 && !out_value) return bad_arg(1, "out_value is null");
+    PeerCtx pc;
+    if (int rc = make_peer_ctx(peers, stats_width, 13, pc)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const long long *as = reinterpret_cast<const long long *>(out_activation_step);
     const unsigned long long *ah = reinterpret_cast<const unsigned long long *>(act_hist);
     if (out_is_f64)
         k_stream_stats<double><<<1, 1024, 0, st>>>((const double *)out_value, (const double *)out_overall, as, ah,
-                                                   n_inst, n_steps, S, A, stats);
+                                                   n_inst, n_steps, S, A, stats, stats_width, accumulate, pc);
     else
         k_stream_stats<float><<<1, 1024, 0, st>>>((const float *)out_value, (const float *)out_overall, as, ah,
-                                                  n_inst, n_steps, S, A, stats);
+                                                  n_inst, n_steps, S, A, stats, stats_width, accumulate, pc);
     DCARL_LAUNCH_CHECK("k_stream_stats");
     return 0;
+}
+
+extern "C" int dcarl_stream_stats(const void *out_value, int out_is_f64, const void *out_overall,
+                                  const int64_t *out_activation_step, const uint64_t *act_hist,
+                                  int64_t n_inst, int64_t n_steps, int32_t S, int32_t A, double *stats,
+                                  dcarl_stream_t stream) {
+    return dcarl_stream_stats_reduce(out_value, out_is_f64, out_overall, out_activation_step, act_hist, n_inst,
+                                     n_steps, S, A, stats, DCARL_STATS_HEADER + (A > 0 ? A : 0), 0, nullptr, stream);
 }

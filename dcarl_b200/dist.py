@@ -3,10 +3,15 @@ all-reduce of the float64 summary-statistics vector per batch (SURVEY section 8e
 
 One process per GPU (torchrun).  NCCL on GPUs, gloo for the CPU tests of this host logic.
 """
+import ctypes as C
 import os
 
 import torch
 import torch.distributed as dist
+
+from . import _abi, _dev
+
+STATS_HEADER = 5   # DCARL_STATS_HEADER
 
 
 def init_from_env(backend=None):
@@ -51,6 +56,106 @@ def allreduce_max(t, group=None):
     return t
 
 
+def allgather(t, group=None):
+    """List of every rank's copy of `t` (rank order); [t] without a process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(out, t, group=group)
+        return out
+    return [t]
+
+
+def _world(group=None):
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+class PeerGroup:
+    """This rank's peer-mapped all-reduce workspace and the mapped workspaces of the other ranks of the
+    NVLink box (include/dcarl_b200.h, dcarl_peer_ctx).  The mapping is plumbing: torch's symmetric-memory
+    allocator does the CUDA IPC exchange; the sum itself runs inside this package's kernels (peer stores
+    over NVLink, a flag per rank, rank-ordered adds).  ``ctx`` is None for a single rank, and when the
+    ranks cannot map each other's memory (``backend`` then says "nccl": callers fall back to
+    torch.distributed.all_reduce)."""
+
+    def __init__(self, n_max, group=None, device=None):
+        self.group, self.n_max = group, int(n_max)
+        self.world = _world(group)
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.ctx, self.backend, self.error = None, "single", None
+        if self.world == 1:
+            return
+        self.backend = "nccl"
+        if self.world > _abi.MAX_PEERS or not torch.cuda.is_available():
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dev = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+            L = _abi.lib()
+            nbytes = int(L.dcarl_peer_ws_bytes(self.world, self.n_max))
+            pg = group if group is not None else dist.group.WORLD
+            if hasattr(symm, "enable_symm_mem_for_group"):
+                try:
+                    symm.enable_symm_mem_for_group(pg.group_name)
+                except Exception:   # noqa: BLE001  (deprecated no-op on newer torch)
+                    pass
+            self.buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.hdl = symm.rendezvous(self.buf, pg)
+            self.buf.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)
+            so, fo, eo = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            L.dcarl_peer_ws_layout(self.world, self.n_max, C.byref(so), C.byref(fo), C.byref(eo))
+            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+            ctx = _abi.PeerCtx()
+            for r in range(self.world):
+                ctx.slots[r] = ptrs[r] + so.value
+                ctx.flags[r] = ptrs[r] + fo.value
+            ctx.epoch = self.buf.data_ptr() + eo.value
+            ctx.rank, ctx.world, ctx.n_max = self.rank, self.world, self.n_max
+            self.ctx, self.backend = ctx, "peer-memory"
+        except Exception as e:   # noqa: BLE001  (no P2P mapping on this box: NCCL carries the sum)
+            self.error = repr(e)
+        # every rank must take the same path
+        ok = torch.tensor([1 if self.ctx is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.ctx, self.backend = None, "nccl"
+
+    def allreduce(self, t, stream=None):
+        """In-place SUM of a float64 CUDA tensor (<= n_max elements) over the ranks."""
+        if self.world == 1:
+            return t
+        if self.ctx is None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return t
+        if t.dtype != torch.float64 or not t.is_contiguous() or t.numel() > self.n_max:
+            raise ValueError("PeerGroup.allreduce: contiguous float64 tensor of at most n_max elements expected")
+        _abi.check(_abi.lib().dcarl_peer_allreduce(_dev.ptr(t), t.numel(), C.byref(self.ctx), _dev.stream_handle(stream)))
+        return t
+
+
+def nccl_comm_ptr(group=None):
+    """The ncclComm_t of torch's NCCL process group as an integer (for dcarl_allreduce_stats), or None."""
+    try:
+        pg = group if group is not None else dist.group.WORLD
+        be = pg._get_backend(torch.device("cuda"))
+        return int(be._comm_ptr())
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def allreduce_stats_abi(stats, group=None, stream=None):
+    """The C-ABI form of the stats all-reduce (dcarl_allreduce_stats: ncclAllReduce on torch's communicator,
+    issued on `stream`).  Falls back to torch.distributed.all_reduce when the communicator is not exposed."""
+    if _world(group) == 1:
+        return stats
+    comm = nccl_comm_ptr(group)
+    if comm is None:
+        return allreduce_stats(stats, group)
+    _abi.check(_abi.lib().dcarl_allreduce_stats(_dev.ptr(stats), stats.numel(), C.c_void_p(comm), _dev.stream_handle(stream)))
+    return stats
+
+
 def barrier():
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
@@ -66,6 +171,88 @@ def box_query_sharded(buf, queries, n_actions, rls_params=None, group=None):
     allreduce_stats(mom, group)
     mv, pick = buf.select(mom, rls_params)
     return mom, mv, pick
+
+
+class ShardedBoxQuery:
+    """Config-4 pattern for repeated queries of one shape: ``run(queries) -> (moments, mean_var, action)``.
+    The buffer is row-sharded over the ranks of `group`, the queries are replicated.  One call is ONE
+    kernel launch (dcarl_box_query): thresholds, the scan of this rank's rows, the sum of the raw moments
+    over ranks through peer memory, and the act_test pick, the last three in the kernel's epilogue.
+    Static output tensors (overwritten by the next call).  Without peer mapping between the ranks the sum
+    goes through NCCL between a scan launch and a select launch."""
+
+    def __init__(self, buf, Q, n_actions, rls_params=None, group=None, peers=None):
+        self.buf, self.Q, self.na, self.group = buf, int(Q), int(n_actions), group
+        self.rp = rls_params or _abi.RlsParams()
+        dev = buf.device
+        self.q = torch.zeros((self.Q, buf.D), dtype=torch.float64, device=dev)
+        self.mom = torch.empty((self.Q, self.na, 3), dtype=torch.float64, device=dev)
+        self.mv = torch.empty((self.Q, self.na, 2), dtype=torch.float64, device=dev)
+        self.pick = torch.empty((self.Q,), dtype=torch.int32, device=dev)
+        self.world = _world(group)
+        L = _abi.lib()
+        self.ws = torch.zeros(int(L.dcarl_box_query_ws(self.Q, buf.D, self.na)) + 16, dtype=torch.uint8, device=dev)
+        self.peers = peers if peers is not None else PeerGroup(min(self.Q, 64) * self.na * 3, group, dev)
+        if self.world == 1:
+            self.path = "one launch: thresholds + scan + totals + select"
+        elif self.peers.ctx is not None:
+            self.path = "one launch: thresholds + scan + peer-memory sum over ranks + select"
+        else:
+            self.path = "scan + NCCL all-reduce of the moments + select"
+
+    def __call__(self, queries):
+        buf = self.buf
+        q = queries if (isinstance(queries, torch.Tensor) and queries.is_cuda and queries.dtype == torch.float64
+                        and queries.is_contiguous()) else _dev.as_device(queries, torch.float64, buf.device)
+        q = q.reshape(self.Q, buf.D)
+        if self.world > 1 and self.peers.ctx is None:
+            buf.moments(q, self.na, out=self.mom)
+            allreduce_stats(self.mom, self.group)
+            buf.select(self.mom, self.rp, out=(self.mv, self.pick))
+            return self.mom, self.mv, self.pick
+        buf.query_fused(q, self.na, self.rp, self.ws, (self.mom, self.mv, self.pick),
+                        self.peers.ctx if self.world > 1 else None)
+        return self.mom, self.mv, self.pick
+
+
+class MixedStreamBatch:
+    """Config-5 pattern: this rank's shard of a batch that mixes scenario shapes (one StreamPlan per shape,
+    e.g. Simulation_1-shaped S=1/A=30 and Simulation_2-shaped S=20/A=11).  ``run(data)`` launches every
+    plan on its rows; the summary kernels chain into ONE vector (the action histogram zero-padded to the
+    widest shape) and the last of them ends with the sum over ranks through peer memory — one collective
+    per batch, fused into the kernel that produces the vector.  ``local_stats`` is this rank's vector
+    before the sum (kept only when ``keep_local``)."""
+
+    def __init__(self, plans, group=None, peers=None, keep_local=True):
+        self.plans, self.group, self.keep_local = list(plans), group, keep_local
+        self.A_max = max(p.A for p in self.plans)
+        self.width = STATS_HEADER + self.A_max
+        dev = self.plans[0].device
+        self.local_stats = torch.zeros(self.width, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros_like(self.local_stats)
+        self.world = _world(group)
+        self.peers = peers if peers is not None else PeerGroup(self.width, group, dev)
+        for p in self.plans:
+            p.want_stats_kernel = False           # the batch runs the summary kernels itself
+
+    def run(self, data, stream=None):
+        """data: one (idx, act, R) triple of CUDA tensors per plan.  Returns the all-reduced stats tensor."""
+        L = _abi.lib()
+        fused = self.world > 1 and self.peers.ctx is not None and not self.keep_local
+        target = self.stats if fused else self.local_stats
+        last = len(self.plans) - 1
+        for k, (plan, (i, a, r)) in enumerate(zip(self.plans, data)):
+            plan.run_device(i, a, r, stream=stream)
+            with torch.cuda.device(plan.device):
+                _abi.check(L.dcarl_stream_stats_reduce(
+                    _dev.ptr(plan.value), int(plan.out_dtype == torch.float64), _dev.ptr(plan.overall),
+                    _dev.ptr(plan.activation_step), _dev.ptr(plan.act_hist), plan.n_inst, plan.n_steps, plan.S, plan.A,
+                    _dev.ptr(target), self.width, int(k > 0),
+                    C.byref(self.peers.ctx) if (fused and k == last) else None, _dev.stream_handle(stream)))
+        if not fused:
+            self.stats.copy_(self.local_stats)
+            self.peers.allreduce(self.stats, stream)
+        return self.stats
 
 
 def stream_sharded(plan, idx, act, R, group=None):

@@ -112,28 +112,51 @@ class BoxBuffer:
             nr[:self.M] = self._ret[:self.M]
             self._state, self._ret = ns, nr
 
-    def _scan(self, row_lo, row_hi, q, n_actions, out, stream=None):
-        """One kernel pass over rows [row_lo, row_hi) (row_lo a multiple of 4: 16-byte aligned tiles)."""
+    def _scan(self, row_lo, row_hi, q, n_actions, out, stream=None, ws=None):
+        """One kernel pass over rows [row_lo, row_hi) (row_lo a multiple of 4: 16-byte aligned tiles).
+        `ws`: a caller-owned threshold workspace (CUDA graphs keep their own: the shared one is replaced
+        when a later call needs more room, which would leave a captured pointer dangling)."""
         L = _abi.lib()
         Q = q.shape[0]
         need = L.dcarl_box_moments_ws(Q, self.D, n_actions)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
+        if ws is None:
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
+            ws = self._ws
+        elif ws.numel() < need:
+            raise ValueError("threshold workspace too small for this query shape")
         sp = C.c_void_p(self._state.data_ptr() + row_lo * (self.D + 1) * 4)
         rp = C.c_void_p(self._ret.data_ptr() + row_lo * 4)
-        _abi.check(L.dcarl_box_moments(sp, rp, row_hi - row_lo, self.D, _dev.ptr(self.dist), _dev.ptr(q), Q,
-                                       n_actions, _dev.ptr(out), _dev.ptr(self._ws), self._ws.numel(),
-                                       _dev.stream_handle(stream)))
+        with torch.cuda.device(self.device):
+            _abi.check(L.dcarl_box_moments(sp, rp, row_hi - row_lo, self.D, _dev.ptr(self.dist), _dev.ptr(q), Q,
+                                           n_actions, _dev.ptr(out), _dev.ptr(ws), ws.numel(),
+                                           _dev.stream_handle(stream)))
         self.last_scanned_rows += (row_hi - row_lo) if Q else 0
 
-    def moments(self, queries, n_actions, out=None, stream=None):
+    def query_fused(self, q, n_actions, rls_params, ws, out, peer_ctx=None, stream=None):
+        """One launch for a whole act_test query pass (dcarl_box_query): q float64 CUDA [Q, D]; ws a
+        zero-initialised uint8 CUDA tensor of dcarl_box_query_ws() bytes that the kernel leaves zeroed;
+        out = (moments [Q, A, 3], mean_var [Q, A, 2], action int32 [Q]) CUDA tensors; peer_ctx sums the
+        moments over the ranks holding the other row shards."""
+        mom, mv, pick = out
+        L = _abi.lib()
+        with torch.cuda.device(self.device):
+            _abi.check(L.dcarl_box_query(
+                _dev.ptr(self._state), _dev.ptr(self._ret), self.M, self.D, _dev.ptr(self.dist), _dev.ptr(q),
+                q.shape[0], n_actions, rls_params or _abi.RlsParams(), _dev.ptr(mom), _dev.ptr(mv), _dev.ptr(pick),
+                C.c_void_p((ws.data_ptr() + 15) & ~15), ws.numel() - 16, C.byref(peer_ctx) if peer_ctx is not None else None,
+                _dev.stream_handle(stream)))
+        self.last_scanned_rows = self.M
+        return mom, mv, pick
+
+    def moments(self, queries, n_actions, out=None, stream=None, ws=None):
         """queries float64 [Q, D] (numpy or CUDA tensor) -> CUDA float64 [Q, n_actions, 3] = (n, sum R, sum R^2).
         One streaming pass over the whole buffer, whatever Q is."""
         q = _dev.as_device(queries, torch.float64, self.device).reshape(-1, self.D).contiguous()
         if out is None:
             out = torch.empty((q.shape[0], n_actions, 3), dtype=torch.float64, device=self.device)
         self.last_scanned_rows = 0
-        self._scan(0, self.M, q, n_actions, out, stream)
+        self._scan(0, self.M, q, n_actions, out, stream, ws)
         return out
 
     # ---- on-device index (SURVEY "next" row f1) ------------------------------------------------
@@ -202,11 +225,10 @@ class BoxBuffer:
         return mv, pick
 
     def query_graph(self, Q, n_actions=8, rls_params=None):
-        """A CUDA-graph replay of (zero moments, threshold prepare, scan, select) for repeated queries
-        of one shape: the per-query cost is one graph launch instead of four kernel launches plus
-        their host overhead (the scan of a 1e7-row shard is ~0.15 ms, shorter than that overhead).
-        Returns ``run(queries) -> (moments, mean_var, action)`` writing into static CUDA tensors; the
-        graph is re-captured automatically when rows were appended to the buffer."""
+        """A CUDA-graph replay of the fused query launch (thresholds + scan + totals + select in one kernel)
+        for repeated queries of one shape: the per-query cost is one graph launch.  Returns
+        ``run(queries) -> (moments, mean_var, action)`` writing into static CUDA tensors; the graph is
+        re-captured automatically when rows were appended to the buffer or its storage moved."""
         return _BoxQueryGraph(self, int(Q), int(n_actions), rls_params or _abi.RlsParams())
 
     def query(self, obs, n_actions=8, rls_params=None):
@@ -221,6 +243,10 @@ class BoxBuffer:
 
 
 class _BoxQueryGraph:
+    """A captured replay of one fused query launch (dcarl_box_query) on static tensors the graph owns:
+    queries in, (moments, mean_var, action) out, its own zeroed workspace.  Re-captured when the buffer
+    grew or moved (append / reserve), never affected by other calls on the same buffer."""
+
     def __init__(self, buf, Q, n_actions, rls_params):
         self.buf, self.Q, self.na, self.rp = buf, Q, n_actions, rls_params
         dev = buf.device
@@ -228,21 +254,25 @@ class _BoxQueryGraph:
         self.mom = torch.empty((Q, n_actions, 3), dtype=torch.float64, device=dev)
         self.mv = torch.empty((Q, n_actions, 2), dtype=torch.float64, device=dev)
         self.pick = torch.empty((Q,), dtype=torch.int32, device=dev)
-        self._graph, self._rows = None, -1
+        self.ws = torch.zeros(int(_abi.lib().dcarl_box_query_ws(Q, buf.D, n_actions)) + 16, dtype=torch.uint8, device=dev)
+        self._graph, self._key = None, None
+
+    def _current_key(self):
+        b = self.buf
+        return (len(b), b._state.data_ptr(), b._ret.data_ptr())
 
     def _record(self):
         buf = self.buf
-        buf.moments(self.q, self.na, out=self.mom)            # sizes the workspace outside the capture
-        buf.select(self.mom, self.rp, out=(self.mv, self.pick))
+        out = (self.mom, self.mv, self.pick)
+        buf.query_fused(self.q, self.na, self.rp, self.ws, out)        # warm-up outside the capture
         torch.cuda.synchronize(buf.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            buf.moments(self.q, self.na, out=self.mom)
-            buf.select(self.mom, self.rp, out=(self.mv, self.pick))
-        self._graph, self._rows = g, len(buf)
+            buf.query_fused(self.q, self.na, self.rp, self.ws, out)
+        self._graph, self._key = g, self._current_key()
 
     def __call__(self, queries):
-        if self._graph is None or self._rows != len(self.buf):
+        if self._graph is None or self._key != self._current_key():
             self._record()
         self.q.copy_(_dev.as_device(queries, torch.float64, self.buf.device).reshape(self.Q, self.buf.D), non_blocking=True)
         self._graph.replay()

@@ -44,6 +44,7 @@ class StreamPlan:
         self.r_dtype, self.out_dtype = r_dtype, out_dtype
         self.want_overall, self.want_stats, self.variant = want_overall, want_stats, int(variant)
         self.key_dtype = key_dtype
+        self.want_stats_kernel = True      # dist.MixedStreamBatch chains the summary kernels of several plans itself
         if key_dtype not in (torch.int32, torch.uint8):
             raise ValueError("key_dtype must be torch.int32 or torch.uint8")
         if key_dtype == torch.uint8:
@@ -109,7 +110,7 @@ class StreamPlan:
                 self._launch(_dev.ptr(idx), _dev.ptr(act), _dev.ptr(R), self.n_inst, _dev.ptr(self.value),
                              _dev.ptr(self.act), _dev.ptr(self.activation_step), _dev.ptr(self.overall),
                              _dev.ptr(self.ws), st)
-                if self.want_stats:
+                if self.want_stats and self.want_stats_kernel:
                     self._stats(st)
         if check:
             self.raise_on_bad_rows()

@@ -59,6 +59,35 @@ typedef struct dcarl_rls_params {
     int32_t min_candidate_visits; /* RLS:141  5 */
 } dcarl_rls_params;
 
+/* ---- multi-GPU: the summary vectors are summed over the ranks of one NVLink / NVSwitch box -----------
+ * The path shards with no data-path exchange: scenario instances (stream) or buffer rows
+ * (box) are partitioned over the GPUs and one small vector is summed per batch — <= 48 KB, so latency
+ * is what counts.  The kernels that produce such a vector can finish with the sum themselves, over
+ * peer-mapped memory: rank r owns a workspace that every other rank has mapped into its address space
+ * (CUDA IPC or symmetric memory; mapping is the host's business), laid out as
+ *   slots [2][world][n_max] float64 | flags [2][world] uint32 | epoch uint32     (dcarl_peer_ws_bytes)
+ * zero-initialised once, before the first call on any rank.  A call writes this rank's vector into its
+ * slot on EVERY rank, raises its flag there, waits for all flags of its own workspace and adds the slots
+ * in rank order (bit-identical sums on every rank, unlike an order-dependent reduction tree).  Two
+ * parities alternate per call; the call counter lives on the device, so launches can be graph-captured.
+ * All ranks must issue the same sequence of calls with the same lengths.  world <= DCARL_MAX_PEERS. */
+#define DCARL_MAX_PEERS 16
+typedef struct dcarl_peer_ctx {
+    void *slots[DCARL_MAX_PEERS];  /* slots[r]: base of rank r's slot area, as mapped in THIS process */
+    void *flags[DCARL_MAX_PEERS];  /* flags[r]: base of rank r's flag area, as mapped in THIS process */
+    void *epoch;                   /* this rank's call counter (device memory) */
+    int32_t rank, world, n_max, pad_;
+} dcarl_peer_ctx;
+size_t dcarl_peer_ws_bytes(int32_t world, int32_t n_max);   /* size of one rank's workspace */
+/* Offsets of the three areas inside a workspace of dcarl_peer_ws_bytes(world, n_max) bytes (host pointers). */
+void dcarl_peer_ws_layout(int32_t world, int32_t n_max, size_t *slots_off, size_t *flags_off, size_t *epoch_off);
+/* data[0..n) (device, float64) <- sum over ranks, in place; one CTA, asynchronous on `stream`. */
+int dcarl_peer_allreduce(double *data, int32_t n, const dcarl_peer_ctx *peers /* host */, dcarl_stream_t stream);
+/* The same sum through NCCL: ncclAllReduce(data, data, n, ncclDouble, ncclSum, comm, stream) on the
+ * library's copy of libnccl (resolved at run time; an error if it cannot be loaded).  `comm` is an
+ * ncclComm_t passed as void*.  (dcarl_allreduce_stats.) */
+int dcarl_allreduce_stats(double *stats, int32_t n, void *comm, dcarl_stream_t stream);
+
 const char *dcarl_last_error(void);
 int dcarl_abi_version(void);
 /* Fills the current device's SM count and compute capability (host pointers). */
@@ -134,6 +163,17 @@ int dcarl_stream_stats(const void *out_value, int out_is_f64, const void *out_ov
                        const int64_t *out_activation_step, const uint64_t *act_hist,
                        int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
                        double *stats /* [DCARL_STATS_HEADER + A] */, dcarl_stream_t stream);
+/* The same reduction ending with the sum over ranks (one kernel: local reduction, then the peer-memory
+ * all-reduce of dcarl_peer_ctx).  stats_width >= DCARL_STATS_HEADER + A: the vector is zero-padded to
+ * that width so that batches mixing shapes with different action counts add up (BASELINE config 5);
+ * accumulate != 0 adds this call's local vector to what `stats` already holds before the sum over ranks
+ * is taken — the caller chains the shapes of a mixed batch and lets only the LAST call of the chain
+ * carry `peers` (the earlier ones pass NULL), so the batch costs one collective. */
+int dcarl_stream_stats_reduce(const void *out_value, int out_is_f64, const void *out_overall,
+                              const int64_t *out_activation_step, const uint64_t *act_hist,
+                              int64_t n_inst, int64_t n_steps, int32_t S, int32_t A,
+                              double *stats, int32_t stats_width, int accumulate,
+                              const dcarl_peer_ctx *peers /* host, nullable */, dcarl_stream_t stream);
 
 /* ---- a8: the {s,a,R} sampler of Data_Generation, DS:12-17, 45-55 -------------------------
  * Draw i: x = loc + sd*z_state[i]; idx = floor(x/span*S); rejected (out_idx = -1, R = 0) when
@@ -164,6 +204,19 @@ int dcarl_box_moments(const float *buf_state, const float *buf_ret, int64_t M, i
                       const double *dist /* [D+1] */, const double *queries /* [Q, D] */,
                       int32_t Q, int32_t n_actions, double *out_moments,
                       void *ws, size_t ws_bytes, dcarl_stream_t stream);
+/* One act_test query pass as ONE launch (RLS:120-157 for Q observations): thresholds in the kernel's
+ * prologue, the scan, and — in the last CTA to finish — the totals, their sum over the ranks that hold the
+ * other row shards (peers != NULL and peers->world > 1; see dcarl_peer_ctx), (mean, var) and the pick.
+ * ws: dcarl_box_query_ws() bytes, 16-byte aligned, zero-initialised ONCE by the caller; every call
+ * leaves it zeroed again (no memset per query).  out_moments [Q, n_actions, 3] holds the totals over all
+ * ranks; out_mean_var / out_action as in dcarl_box_select (each nullable). */
+size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions);
+int dcarl_box_query(const float *buf_state, const float *buf_ret, int64_t M, int32_t D,
+                    const double *dist /* [D+1] */, const double *queries /* [Q, D] */,
+                    int32_t Q, int32_t n_actions, const dcarl_rls_params *p /* host */,
+                    double *out_moments, double *out_mean_var, int32_t *out_action,
+                    void *ws, size_t ws_bytes, const dcarl_peer_ctx *peers /* host, nullable */,
+                    dcarl_stream_t stream);
 /* Moments -> (mean, var) with the (-1,-1) sentinel for n == 0 (RLS:169-170) and the
  * act_test pick: first candidate 1..n_actions-1 passing the gate and the z-test, else 0.
  * out_mean_var [Q, n_actions, 2] and out_action [Q] are each nullable. */

@@ -203,6 +203,76 @@ def test_query_graph_replay_matches_the_plain_path_and_tracks_appends():
             buf.append(vs[half:], ret[half:])          # the next call must re-capture with the new row count
 
 
+def test_query_graph_is_not_disturbed_by_other_calls_on_the_buffer():
+    """The captured launch owns its workspace: a larger moments() call between two replays (which replaces
+    the buffer's shared threshold workspace) or a second graph must not change what a replay returns."""
+    rng = np.random.default_rng(22)
+    centers, vs, ret = _clustered(rng, n_centers=6)
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, ret)
+    run = buf.query_graph(2, 8)
+    want = _oracle_nmv(vs, ret, centers[:2], 8)
+    mom, _, pick = run(centers[:2])
+    first = (mom.clone(), pick.clone())
+    big = np.repeat(centers, 40, axis=0)                                 # Q = 240: a much larger workspace
+    buf.moments(big, 8)
+    other = buf.query_graph(6, 8)
+    other(centers)
+    junk = torch.full((1 << 20,), 0x7f, dtype=torch.uint8, device="cuda")  # reuse whatever the allocator freed
+    mom, _, pick = run(centers[:2])
+    torch.cuda.synchronize()
+    assert torch.equal(mom, first[0]) and torch.equal(pick, first[1])
+    assert np.array_equal(mom[:, :, 0].cpu().numpy(), want[:, :, 0])
+    del junk
+
+
+def test_fused_query_launch_matches_the_three_step_path():
+    """dcarl_box_query (thresholds + scan + totals + select in one launch, workspace left zeroed) against
+    dcarl_box_moments + dcarl_box_select, including the global-atomics bins, chunked queries, repeated
+    calls on one workspace and an empty buffer."""
+    from dcarl_b200 import dist as dd
+    rng = np.random.default_rng(23)
+    centers, vs, ret = _clustered(rng, n_centers=40, n_actions=12, max_rows=30)
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, ret)
+    for Q, na in ((1, 8), (7, 12), (40, 12), (40, 256)):                 # 40 x 256 bins: global atomics; > smem: chunks
+        q = torch.from_numpy(np.ascontiguousarray(centers[:Q])).cuda()
+        mom = buf.moments(q, na)
+        mv, pick = buf.select(mom)
+        fq = dd.ShardedBoxQuery(buf, Q, na)
+        for rep in range(3):
+            fmom, fmv, fpick = fq(q)
+            torch.cuda.synchronize()
+            assert torch.equal(fmom[:, :, 0], mom[:, :, 0]) and torch.equal(fpick, pick), (Q, na, rep)
+            assert float((fmom - mom).abs().max()) < 1e-9 and float((fmv - mv).abs().max()) < 1e-9
+        assert int(fq.ws.view(torch.int32).abs().sum()) == 0            # accumulator and ticket came back zeroed
+        ref = _oracle_nmv(vs, ret, centers[:Q], na)
+        assert np.array_equal(fmom[:, :, 0].cpu().numpy(), ref[:, :, 0])
+    empty = dc.BoxBuffer(20)
+    fq = dd.ShardedBoxQuery(empty, 3, 8)
+    fmom, fmv, fpick = fq(centers[:3])
+    torch.cuda.synchronize()
+    assert float(fmom.abs().sum()) == 0 and bool((fmv == -1).all()) and bool((fpick == 0).all())
+
+
+def test_stats_chain_of_a_mixed_batch():
+    """dcarl_stream_stats_reduce: zero-padded width and accumulation across the shapes of a mixed batch."""
+    from dcarl_b200 import dist as dd
+    from helpers import synth_streams
+    i1, a1, R1 = synth_streams(24, 300, 1, 30, seed=1, r_dtype=np.float32, live_actions=11)
+    i2, a2, R2 = synth_streams(24, 300, 20, 11, seed=2, r_dtype=np.float32)
+    p1, p2 = dc.StreamPlan(24, 300, 1, 30), dc.StreamPlan(24, 300, 20, 11)
+    d1 = [torch.from_numpy(x).cuda() for x in (i1, a1, R1)]
+    d2 = [torch.from_numpy(x).cuda() for x in (i2, a2, R2)]
+    want = dc.merge_stats([p1.run_device(*d1).stats.clone(), p2.run_device(*d2).stats.clone()])
+    for keep in (True, False):
+        mb = dd.MixedStreamBatch([p1, p2], keep_local=keep)
+        got = mb.run([d1, d2]).clone()
+        got2 = mb.run([d1, d2])
+        torch.cuda.synchronize()
+        assert got.numel() == 35 and torch.equal(got, want) and torch.equal(got2, want)
+
+
 def test_batched_add_data_matches_the_reference_deque():
     """SURVEY next-row f2: many transition streams at once against the literal deque restatement
     (RLS.py:185-215), including streams with no done, several dones, and fewer than 10 steps."""

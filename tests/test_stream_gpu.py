@@ -168,9 +168,10 @@ def test_constant_and_nearly_constant_cells():
     s2 = np.cumsum(np.full(400, c * c))[n - 1]
     out = torch.empty(len(n), dtype=torch.float64, device="cuda")
     t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", d)
-    _abi.check(_abi.lib().dcarl_cell_values(dc._dev.ptr(t(n, torch.int32)), dc._dev.ptr(t(s1, torch.float64)),
-                                            dc._dev.ptr(t(s2, torch.float64)), dc._dev.ptr(t(np.ones(len(n)), torch.int32)),
+    dn, d1, d2, da = t(n, torch.int32), t(s1, torch.float64), t(s2, torch.float64), t(np.ones(len(n)), torch.int32)
+    _abi.check(_abi.lib().dcarl_cell_values(dc._dev.ptr(dn), dc._dev.ptr(d1), dc._dev.ptr(d2), dc._dev.ptr(da),
                                             len(n), _abi.Params(), dc._dev.ptr(out), dc._dev.stream_handle()))
+    torch.cuda.synchronize()
     ch = 150.0 * np.sqrt(np.log(20.0) / 2)
     want = np.minimum(c - ch / np.sqrt(n), c - ch / np.sqrt(n + 1.0))   # min(lower, CI lower) with sigma = 0
     assert np.abs(out.cpu().numpy() - want).max() < 1e-11

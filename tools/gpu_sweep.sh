@@ -17,3 +17,8 @@ done
 timeout 300 ncu --metrics $M --clock-control none -k regex:k_stream_rows --csv --log-file gpurun_out/sweep_ncu.csv \
     python tools/stream_sweep.py --once > gpurun_out/sweep_ncu.log 2>&1
 echo "ncu exit $?"; tail -3 gpurun_out/sweep_ncu.log | cut -c1-300
+if [ -n "$FULL" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_stream_rows -c 1 -f -o gpurun_out/rows_${FULL} \
+    python tools/stream_sweep.py --once > gpurun_out/ncu_rows_full.log 2>&1
+echo "full capture exit $?"
+fi

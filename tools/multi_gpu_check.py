@@ -66,7 +66,27 @@ lo, hi = dd.shard_range(M, rank, world)
 shard = dc.BoxBuffer(20, capacity=hi - lo)
 shard.append(rows[lo:hi], ret[lo:hi])
 rp = dc.RlsParams(visited_times_thres=10)
-mom, mv, pick = dd.box_query_sharded(shard, q, NA, rp)
+mom, mv, pick = dd.box_query_sharded(shard, q, NA, rp)            # scan + all-reduce + select (three steps)
+fq = dd.ShardedBoxQuery(shard, Q, NA, rp)                          # one launch, sum over ranks through peer memory
+for _ in range(3):                                                 # repeated calls: the workspace must come back zeroed
+    fmom, fmv, fpick = fq(q)
+torch.cuda.synchronize()
+out["box_fused_path"] = fq.path
+out["box_fused_equals_unfused"] = bool(torch.equal(fmom[:, :, 0], mom[:, :, 0]) and torch.equal(fpick, pick)
+                                       and float((fmom - mom).abs().max()) < 1e-9)
+# the peer-memory sum against NCCL on random vectors, twenty calls back to back (both parities, epochs)
+pg = dd.PeerGroup(4096)
+peer_ok = True
+for it in range(20):
+    v = torch.randn(1000 + it, generator=torch.Generator(device=dev).manual_seed(100 * rank + it), device=dev, dtype=torch.float64)
+    w = v.clone()
+    pg.allreduce(v)
+    torch.distributed.all_reduce(w) if world > 1 else None
+    peer_ok = peer_ok and float((v - w).abs().max()) < 1e-12
+gath = dd.allgather(v)
+out["peer_backend"] = pg.backend
+out["peer_allreduce_matches_nccl"] = bool(peer_ok)
+out["peer_allreduce_bitwise_equal_on_all_ranks"] = bool(all(torch.equal(gath[0], x) for x in gath))
 whole = dc.BoxBuffer(20, capacity=M)
 whole.append(rows, ret)
 mom1 = whole.moments(q, NA)
@@ -109,9 +129,11 @@ if os.environ.get("TIMINGS", "1") == "1":
     del st
     q1 = centers[:1].double().contiguous()
     ms = timed(lambda: dd.box_query_sharded(b4, q1, 256), 50)
-    out["config4"] = {"rows_total": M4 * world, "ms_per_query_pass": ms, "rows_per_s": M4 * world / (ms * 1e-3),
-                      "achieved_GBs_per_gpu": M4 * 88 / (ms * 1e-3) / 1e9,
-                      "includes": "scan + all-reduce of 256x3 float64 moments + select"}
+    f4 = dd.ShardedBoxQuery(b4, 1, 256)
+    ms_f = timed(lambda: f4(q1), 50)
+    out["config4"] = {"rows_total": M4 * world, "ms_per_query_pass": ms_f, "rows_per_s": M4 * world / (ms_f * 1e-3),
+                      "achieved_GBs_per_gpu": M4 * 88 / (ms_f * 1e-3) / 1e9, "path": f4.path,
+                      "ms_three_step_path": ms, "three_step_path": "scan + NCCL all-reduce of 256x3 float64 moments + select"}
     del b4
     ne, ns = 16384, 500                                     # per GPU: 16384 Sim1-shaped + 16384 Sim2-shaped
     i1 = torch.zeros((ne, ns), dtype=torch.int32, device=dev)
@@ -126,7 +148,15 @@ if os.environ.get("TIMINGS", "1") == "1":
         r1 = p1.run_device(i1, a1, R1)
         r2 = p2.run_device(i2, a2, R2)
         return dd.allreduce_stats(dc.merge_stats([r1.stats, r2.stats]))
-    ms = timed(c5, 50)
+    ms_old = timed(c5, 50)
+    want5 = c5().clone()
+    mb = dd.MixedStreamBatch([p1, p2], keep_local=False)
+    ms = timed(lambda: mb.run([(i1, a1, R1), (i2, a2, R2)]), 50)
+    got5 = mb.run([(i1, a1, R1), (i2, a2, R2)])
+    torch.cuda.synchronize()
+    out["config5_fused_stats_match"] = bool(torch.equal(got5[2:], want5[2:]) and
+                                            float(((got5[:2] - want5[:2]).abs() / want5[:2].abs().clamp_min(1)).max()) < 1e-12)
+    out["config5_ms_unfused"] = ms_old
     steps = 2 * ne * ns * world
     out["config5"] = {"scenario_steps_total": steps, "ms_per_batch": ms, "scenario_steps_per_s": steps / (ms * 1e-3),
                       "achieved_GBs_per_gpu": 2 * ne * ns * 24 / (ms * 1e-3) / 1e9}

@@ -48,7 +48,7 @@ def main():
             ins.append((int(m.group(1), 16), m.group(2).strip(), cur))
     best = None
     for i, (a, s, _) in enumerate(ins):
-        m = re.search(r"BRA(\.U)?\s+(!?U?P\d+,\s*)?`\((\.L_x_\d+)\)", s)
+        m = re.search(r"BRA(\.U)\s+(!?U?P\d+,\s*)?`\((\.L_x_\d+)\)", s)   # uniform backward branch = a warp-uniform loop
         if m and m.group(3) in labels and labels[m.group(3)] < i:
             span = i - labels[m.group(3)]
             if best is None or span > best[0]:
