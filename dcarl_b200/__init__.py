@@ -8,6 +8,7 @@ behind a C ABI (include/dcarl_b200.h, dcarl_b200/csrc/*.cu, bound in _abi.py wit
     Data_Generation, add_an_act_data, random_state_norm       data_sampling.py
     RLS, BoxBuffer                                            stable_baselines/deepq/RLS.py
     rollout_cv                                                constant-velocity surrogate
+    rollout_candidates, collect_and_select                    dqn_value_collect.py:86-145 + TestScenario_Town03.py:403-422
     JunctionTrajectoryPlanner, frenet_plan, Routes            Agent/zzz/JunctionTrajectoryPlanner.py (+ predict.py)
 
 There is no CPU fallback: a compute call without the built library or without a CUDA device raises.
@@ -18,7 +19,7 @@ from .stream import StreamPlan, StreamResult, merge_stats, simulate, stream_boun
 from .sampling import (Data_Generation, add_an_act_data, generate, random_state_manual,  # noqa: F401
                        random_state_norm, sample_returns, sample_returns_philox)
 from .rls import RLS, BoxBuffer, VISITED_STATE_DIST  # noqa: F401
-from .rollout import rollout_cv  # noqa: F401
+from .rollout import collect_and_select, rollout_candidates, rollout_cv, rollout_params  # noqa: F401
 from .frenet import (FrenetParams, FrenetResult, JunctionTrajectoryPlanner, Routes, TrajectoryAction,  # noqa: F401
                      dense_polyline2d, frenet_params, frenet_plan, frenet_start)
 from .io import load_rls_buffer, load_sim_data, save_rls_buffer  # noqa: F401

@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "lib", "libdcarl_b200.so")
+# DCARL_B200_LIB selects another build of the same library (kernel A/B runs, tools/gpu_ab.sh)
+LIB_PATH = os.environ.get("DCARL_B200_LIB") or os.path.join(_DIR, "lib", "libdcarl_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "dcarl_b200.h")
 _lib = None
 ABI_VERSION = 2
@@ -51,6 +52,14 @@ class PeerCtx(C.Structure):
     """dcarl_peer_ctx — peer-mapped all-reduce workspaces of the ranks of one NVLink box."""
     _fields_ = [("slots", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS), ("epoch", C.c_void_p),
                 ("rank", C.c_int32), ("world", C.c_int32), ("n_max", C.c_int32), ("pad_", C.c_int32)]
+
+
+class RolloutParams(C.Structure):
+    """dcarl_rollout_params — constants of the candidate-trajectory rollout (see the header)."""
+    _fields_ = [("dt", C.c_double), ("robot_radius", C.c_double), ("move_gap", C.c_double),
+                ("ticks_per_point", C.c_double), ("collision_reward", C.c_double), ("pass_y", C.c_double),
+                ("stuck_speed", C.c_double), ("stay_thres", C.c_double), ("n_pred", C.c_int32),
+                ("obstacles_considered", C.c_int32)]
 
 
 FRENET_MAX_D, FRENET_MAX_T, FRENET_MAX_V = 16, 4, 8
@@ -106,6 +115,9 @@ SIGNATURES = {
     "dcarl_add_data_counts": (_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dcarl_add_data_rows": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _d, _vp, _vp, _vp]),
     "dcarl_rollout_cv": (_int, [_vp, _vp, _i64, _i32, _f, _f, _f, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "dcarl_default_rollout_params": (None, [C.POINTER(RolloutParams)]),
+    "dcarl_rollout_candidates": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, C.POINTER(RolloutParams),
+                                        _vp, _vp, _vp, _vp]),
     "dcarl_default_frenet_params": (None, [C.POINTER(FrenetParams)]),
     "dcarl_spline_build": (_int, [_vp, _vp, _i32, _vp, _vp]),
     "dcarl_frenet_start": (_int, [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),

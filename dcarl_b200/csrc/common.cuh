@@ -80,20 +80,37 @@ __device__ __forceinline__ void st_stream(double *p, double v) {
 }
 
 // Shared-memory accesses by 32-bit shared-space address (no generic-pointer window arithmetic).
+#if defined(DCARL_V_GENERIC_HOT)   // A/B variant: the same accesses through generic pointers
 __device__ __forceinline__ void lds_v2f64(unsigned a, double &x, double &y) {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+    const double2 v = *reinterpret_cast<const double2 *>(__cvta_shared_to_generic(a));
+    x = v.x; y = v.y;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) { return *reinterpret_cast<const double *>(__cvta_shared_to_generic(a)); }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { *reinterpret_cast<double *>(__cvta_shared_to_generic(a)) = v; }
+__device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) {
+    *reinterpret_cast<double2 *>(__cvta_shared_to_generic(a)) = make_double2(x, y);
+}
+#else
+#if defined(DCARL_V_NOCLOBBER)
+#define DCARL_SMEM_CLOBBER
+#else
+#define DCARL_SMEM_CLOBBER : "memory"
+#endif
+__device__ __forceinline__ void lds_v2f64(unsigned a, double &x, double &y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) DCARL_SMEM_CLOBBER);
 }
 __device__ __forceinline__ double lds_f64(unsigned a) {
     double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) DCARL_SMEM_CLOBBER);
     return v;
 }
 __device__ __forceinline__ void sts_f64(unsigned a, double v) {
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) DCARL_SMEM_CLOBBER);
 }
 __device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) DCARL_SMEM_CLOBBER);
 }
+#endif
 
 __device__ __forceinline__ double shfl_f64(double v, int src) {
     return __shfl_sync(FULL_MASK, v, src);

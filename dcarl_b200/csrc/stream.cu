@@ -100,8 +100,14 @@ __device__ __forceinline__ double cell_value_e(const NEntry e0, const NEntry e1,
     const double t = __dmul_rn(mean, mean);
     const double var = __fma_rn(s2, e0.inv_n, -t);
     // var <= t * n * 2^-50  <=>  var - (t * 2^-50) * n <= 0
-    const double sigma = __fma_rn(-__dmul_rn(t, 8.8817841970012523e-16 /* 2^-50 */), dn, var) > 0.0
-                             ? __dmul_rn(var, rsqrt_pos(var)) : 0.0;
+    // var <= t * n * 2^-50  <=>  var - (t * 2^-50) * n <= 0.  The 1/sqrt chain does not wait for the
+    // test: it runs on whatever var holds (garbage for var <= 0) and the select discards it.
+    const double sd = __dmul_rn(var, rsqrt_pos(var));
+#ifdef DCARL_V_ABS_CLAMP
+    const double sigma = var > 1e-280 ? sd : 0.0;
+#else
+    const double sigma = __fma_rn(-__dmul_rn(t, 8.8817841970012523e-16 /* 2^-50 */), dn, var) > 0.0 ? sd : 0.0;
+#endif
     const double ci = __fma_rn(__dadd_rn(__fma_rn(-4.0, sigma, mean), s1), e1.inv_n, -e1.hn);
     return dmin(x, is_rule ? cap : ci);
 }

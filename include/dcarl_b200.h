@@ -252,6 +252,41 @@ int dcarl_rollout_cv(const float *state0, const int32_t *action, int64_t n, int3
                      int32_t n_actions, float *out_return, int32_t *out_steps, int32_t *out_term,
                      dcarl_stream_t stream);
 
+/* ---- candidate-trajectory rollout: the episode return of every action of a scenario ------------
+ * The reference's collector (Data_From_Carla/Agent/drl_library/dqn/dqn_value_collect.py:86-145) locks in
+ * one planner candidate per episode (action 0 = the brake trajectory, c+1 = candidate c, JTP:132-140),
+ * follows it in CARLA and records (state, action, sum of step rewards).  Here the episode is idealised
+ * kinematically on the planner's own outputs (dcarl_frenet_plan: out_paths, out_n_valid, out_cost): the
+ * ego is at point k of the trajectory at time k*dt, its speed the distance between consecutive points / dt;
+ * the other vehicles move at constant velocity (PRD:96-100).  Per point: reward
+ * ticks_per_point * 0.1 * sqrt(v) (TS:403-404; TS = Test_Scenarios/TestScenario_Town03.py); a collision —
+ * the planner's own predicate, PRD:49-59, at t = 2, 4, ... < min(len - 1, n_pred - 1) against the front /
+ * back circles of the nearest vehicles — replaces it by collision_reward and ends the episode (TS:407-410);
+ * y < pass_y ends it (TS:414-415, :196-201); otherwise a speed below stuck_speed for more than stay_thres
+ * seconds ends it with reward 0 (TS:419-422, :182-194).  The brake action stands still at the first point
+ * over the cheapest candidate's horizon (JTP:147-150).
+ *   out_return [n, C+1] float64, out_steps [n, C+1] points consumed,
+ *   out_term   [n, C+1] 0 = trajectory ran out, 1 = collision, 2 = pass, 3 = stuck. */
+typedef struct dcarl_rollout_params {
+    double dt;                 /* JTP:19   0.3 */
+    double robot_radius;       /* JTP:29   1 */
+    double move_gap;           /* JTP:31   1 */
+    double ticks_per_point;    /* dt / simulator tick (TS:84: 0.05 s) = 6 */
+    double collision_reward;   /* TS:409   -100 */
+    double pass_y;             /* TS:198   73.7 (NaN: never) */
+    double stuck_speed;        /* TS:188   0.1 */
+    double stay_thres;         /* TS:182   2 s */
+    int32_t n_pred;            /* PRD:91   len(np.arange(0, MAXT, DT)) = 15 */
+    int32_t obstacles_considered; /* JTP:28 4 */
+} dcarl_rollout_params;
+void dcarl_default_rollout_params(dcarl_rollout_params *p);   /* host pointer */
+int dcarl_rollout_candidates(const double *paths /* [n, C, Tm, 2] */, const int32_t *n_valid /* [n, C] */,
+                             const double *cost /* [n, C] */, const double *ego_xy /* [n, 2] */,
+                             const double *obs /* [n, max_obs, 5] */, const int32_t *n_obs /* [n] */,
+                             int32_t max_obs, int64_t n, int32_t C, int32_t Tm,
+                             const dcarl_rollout_params *p /* host */, double *out_return,
+                             int32_t *out_steps, int32_t *out_term, dcarl_stream_t stream);
+
 /* ---- "next" row f3: Frenet candidate trajectories + collision-checked selection --------------
  * One planning tick of JunctionTrajectoryPlanner (JTP:103-140) for n independent scenarios.
  *

@@ -173,3 +173,79 @@ def data_generation(u_states, u_action_values, z_state, acts, z_ret,
         data.append([int(idx), states[idx], int(act), float(action_values[idx][act] + 50 * z_ret[j])])  # DS:55,9
         j += 1
     return np.array(data), np.array(action_values), np.array(states)
+
+
+# ---- candidate-trajectory rollout (closed loop of the collector) ---------------------------------------
+# DVC = Simulation_testing/Simulation_Data_Collection/Data_From_Carla/Agent/drl_library/dqn/dqn_value_collect.py
+# TS  = .../Data_From_Carla/Test_Scenarios/TestScenario_Town03.py
+# PRD = .../Data_From_Carla/Agent/zzz/predict.py,  JTP = .../Agent/zzz/JunctionTrajectoryPlanner.py
+# Written from those lines (not from the CUDA kernel).  CARLA itself cannot run here: the ego is placed AT
+# point k of the locked-in trajectory at time k*DT and its speed is the distance between consecutive
+# points / DT; every rule below is the reference's.
+def predict_circles(ego_xy, vehicles, considered, move_gap):
+    """PRD:64-110.  vehicles: rows [x, y, vx, vy, yaw].  Returns [(x0, y0, vx, vy)] for the front and the
+    back circle of each of the `considered` vehicles nearest to the ego (sorted() is stable: PRD:78)."""
+    d = [(float(np.linalg.norm(np.array([v[0], v[1]]) - np.asarray(ego_xy))), i) for i, v in enumerate(vehicles)]   # PRD:72-76
+    order = sorted(d, key=lambda t: t[0])                                                                            # PRD:78
+    out = []
+    for _, i in order[:considered]:                                                                                  # PRD:80-83
+        x, y, vx, vy, yaw = vehicles[i]
+        out.append((x + math.cos(yaw) * move_gap, y + math.sin(yaw) * move_gap, vx, vy))                            # PRD:103-104
+        out.append((x - math.cos(yaw) * move_gap, y - math.sin(yaw) * move_gap, vx, vy))                            # PRD:105-106
+    return out
+
+
+def rollout_episode(xs, ys, brake, circles, n_pred, dt=0.3, radius=1.0, ticks_per_point=6.0,
+                    collision_reward=-100.0, pass_y=73.7, stuck_speed=0.1, stay_thres=2.0):
+    """One episode along the trajectory (xs, ys) [DVC:106-113 keeps following the trajectory locked in at the
+    trigger].  `brake`: the backup trajectory, i.e. the same points with every desired speed zeroed
+    (JTP:147-150) — the ego stands still at the first point.  Returns (return, points consumed, term) with
+    term 0 = trajectory ran out, 1 = collision, 2 = pass, 3 = stuck."""
+    n = len(xs)
+    episode_reward = 0.0
+    stuck_time = 0.0                       # TS:183-185: the first call only arms the clock
+    for k in range(n):
+        if brake:
+            x, y, v = xs[0], ys[0], 0.0
+        else:
+            x, y = xs[k], ys[k]
+            k0 = k if k + 1 < n else k - 1
+            v = math.hypot(xs[k0 + 1] - xs[k0], ys[k0 + 1] - ys[k0]) / dt if n >= 2 else 0.0
+        reward = ticks_per_point * (math.sqrt(v) * 0.1)                          # TS:403-404, per simulator tick
+        done, term = False, 0
+        # PRD:49-59: for t in range(2, min(len(fp.x) - 1, len(path.t) - 1), 2), any circle within the radius
+        if k in range(2, min(n - 1, n_pred - 1), 2):
+            for (cx, cy, vx, vy) in circles:
+                px, py = cx + k * dt * vx, cy + k * dt * vy                      # PRD:99-100
+                if (px - x) ** 2 + (py - y) ** 2 <= radius ** 2:                 # PRD:57-58
+                    reward, done, term = collision_reward, True, 1               # TS:407-410
+                    break
+        if y < pass_y:                                                           # TS:414-415, :198
+            done = True
+            term = term or 2
+        else:                                                                    # TS:419 elif
+            now = k * dt
+            if k > 0 and v < stuck_speed:                                        # TS:188
+                if now - stuck_time > stay_thres:                                # TS:189-190
+                    reward, done, term = 0.0, True, 3                            # TS:420-422
+            else:
+                stuck_time = now                                                 # TS:192 (and :184 on the first call)
+        episode_reward += reward                                                 # DVC:119
+        if done:
+            return episode_reward, k + 1, term
+    return episode_reward, n, 0
+
+
+def rollout_candidates(paths, n_valid, cost, ego_xy, vehicles, considered=4, move_gap=1.0, **kw):
+    """All C+1 actions of one scenario (DVC:144-145 cycles used_action over 0..len(candidates)).
+    paths [C, Tm, 2], n_valid [C], cost [C].  Action 0 = brake over the cheapest candidate's points
+    (JTP:151-153: sorted by cost, stable), action c+1 = candidate c (JTP:139)."""
+    circles = predict_circles(ego_xy, vehicles, considered, move_gap)
+    C = len(n_valid)
+    cheapest = sorted(range(C), key=lambda c: cost[c])[0]
+    out = []
+    for act in range(C + 1):
+        c = cheapest if act == 0 else act - 1
+        n = int(n_valid[c])
+        out.append(rollout_episode(list(paths[c, :n, 0]), list(paths[c, :n, 1]), act == 0, circles, **kw))
+    return out

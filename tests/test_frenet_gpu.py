@@ -180,3 +180,91 @@ def test_drop_in_planner_class_reproduces_the_reference_tick(g):
         assert np.abs(action.trajectory - g["traj_xy"][i, :n]).max() < 1e-8
         assert np.abs(np.array(action.desired_speed) - g["traj_speed"][i]).max() < 1e-8
         assert len(planner.all_trajectory) == g["cost"].shape[1]
+
+
+# ---- candidate rollout + the closed collect -> buffer -> confidence loop ---------------------------------
+def _rollout_kw(g, r, i=None):
+    return dict(dt=float(g["const_DT"]), robot_radius=float(g["const_ROBOT_RADIUS"]), move_gap=float(g["const_MOVE_GAP"]),
+                ticks_per_point=float(r["ticks_per_point"]), collision_reward=float(r["collision_reward"]),
+                stuck_speed=float(r["stuck_speed"]), stay_thres=float(r["stay_thres"]), n_pred=15,
+                obstacles_considered=int(g["const_OBSTACLES_CONSIDERED"]))
+
+
+def test_candidate_rollout_matches_episodes_rolled_with_the_reference_objects(g, golden):
+    """dcarl_rollout_candidates on the planner's own device outputs against tests/golden/rollout.npz (the
+    reference's planner + predict.check_collision drove those episodes, tools/make_golden_rollout.py)."""
+    import torch
+    r = golden("rollout")
+    n = int(r["n_cases"])
+    p = params_from_golden(g, fr.frenet_params)
+    b = golden_batch(g)
+    routes = _routes_from(b)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+    for pass_y in np.unique(r["pass_y"]):                               # one launch per pass threshold (per route)
+        m = np.nonzero(r["pass_y"] == pass_y)[0]
+        d = (t(b["path_id"][m], torch.int32), t(b["start"][m], torch.float64), t(b["ego_xy"][m], torch.float64),
+             t(b["obs"][m], torch.float64), t(b["n_obs"][m], torch.int32))
+        plan = fr.frenet_plan(routes, *d, p, want_paths=True)
+        ret, steps, term = dc.rollout_candidates(plan, d[2], d[3], d[4], dc.rollout_params(pass_y=float(pass_y), **_rollout_kw(g, r)))
+        assert np.array_equal(steps.cpu().numpy(), r["steps"][m]) and np.array_equal(term.cpu().numpy(), r["term"][m])
+        assert np.abs(ret.cpu().numpy() - r["ret"][m]).max() < 1e-9
+    assert n == 64
+
+
+def test_candidate_rollout_random_scenarios_vs_oracle():
+    import torch
+    from oracle import pyref
+    rng = np.random.default_rng(31)
+    knots, off = synth_routes(rng, 7)
+    routes = fr.Routes([knots[off[i]:off[i + 1]] for i in range(7)])
+    pid, start, ego, obs, n_obs = synth_scenarios(rng, 400, knots, off, max_obs=6)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+    d = (t(pid, torch.int32), t(start, torch.float64), t(ego, torch.float64), t(obs, torch.float64), t(n_obs, torch.int32))
+    plan = fr.frenet_plan(routes, *d, want_paths=True)
+    pass_y = float(np.median(ego[:, 1]))
+    rp = dc.rollout_params(pass_y=pass_y, stay_thres=0.5)
+    ret, steps, term = (x.cpu().numpy() for x in dc.rollout_candidates(plan, d[2], d[3], d[4], rp))
+    paths, nv, cost = plan.paths.cpu().numpy(), plan.n_valid.cpu().numpy(), plan.cost.cpu().numpy()
+    for i in range(400):
+        want = pyref.rollout_candidates(paths[i], nv[i], cost[i], ego[i], [tuple(v) for v in obs[i, :n_obs[i]]], considered=4,
+                                        move_gap=1.0, n_pred=15, dt=0.3, radius=1.0, pass_y=pass_y, stay_thres=0.5)
+        assert [w[1] for w in want] == steps[i].tolist() and [w[2] for w in want] == term[i].tolist(), i
+        assert np.abs(np.array([w[0] for w in want]) - ret[i]).max() < 1e-9
+    assert set(np.unique(term)) >= {0, 1, 2}
+
+
+def test_collect_and_select_closes_the_loop_on_the_device():
+    """planner -> candidate rollout -> buffer rows -> box-kernel confidence -> act_test, one Python call."""
+    import torch
+    from oracle import cport
+    rng = np.random.default_rng(41)
+    knots, off = synth_routes(rng, 3)
+    routes = fr.Routes([knots[off[i]:off[i + 1]] for i in range(3)])
+    # 12 distinct scenarios, each repeated 30 times with small jitter so that the boxes of a scenario overlap
+    pid, start, ego_xy, obs, n_obs = synth_scenarios(rng, 12, knots, off, max_obs=3)
+    rep = 30
+    pid, n_obs = np.repeat(pid, rep), np.repeat(n_obs, rep)
+    obs = np.repeat(obs, rep, axis=0)
+    obs[:, :, :2] += rng.normal(0, 0.05, (len(pid), obs.shape[1], 2))
+    u = rng.uniform(-np.pi, np.pi, 12)
+    v = rng.uniform(3, 9, 12)
+    ego = np.repeat(np.c_[ego_xy, v * np.cos(u), v * np.sin(u), v], rep, axis=0)
+    ego[:, :2] += rng.normal(0, 0.05, (len(pid), 2))
+    buf = dc.BoxBuffer(20)
+    rls = dc.RlsParams(visited_times_thres=10)
+    out = dc.collect_and_select(routes, pid, ego, obs, n_obs, buf, rollout=dc.rollout_params(pass_y=float("nan")), rls_params=rls)
+    n, A = len(pid), out["ret"].shape[1]
+    assert A == 11 and len(buf) == out["rows_appended"] == n * A
+    st, ret = buf.state.cpu().numpy(), buf.ret.cpu().numpy()
+    # the rows are (state (+) action, episode return), scenario-major (dqn_value_collect.py:128-137)
+    assert np.array_equal(st[:, 20].reshape(n, A), np.tile(np.arange(A, dtype=np.float32), (n, 1)))
+    assert np.array_equal(ret.reshape(n, A), out["ret"].cpu().numpy().astype(np.float32))
+    assert np.array_equal(st[::A, :20], out["state"].cpu().numpy().astype(np.float32))
+    # the confidence query of every scenario's state against the oracle on the same rows
+    ref = cport.box_raw(st, ret, dc.VISITED_STATE_DIST[0], out["state"].cpu().numpy(), A)
+    assert np.array_equal(out["n"].cpu().numpy(), ref[:, :, 0]) and ref[:, 0, 0].min() >= 10
+    nn = np.maximum(ref[:, :, 0], 1)
+    nmv = np.stack([ref[:, :, 0], np.where(ref[:, :, 0] > 0, ref[:, :, 1] / nn, -1.0),
+                    np.where(ref[:, :, 0] > 0, np.maximum(ref[:, :, 2] / nn - (ref[:, :, 1] / nn) ** 2, 0), -1.0)], 2)
+    assert np.array_equal(out["action"].cpu().numpy(), cport.box_select(nmv, visited_times_thres=10))
+    assert np.abs(out["mean"].cpu().numpy() - nmv[:, :, 1]).max() < 1e-9
