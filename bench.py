@@ -410,11 +410,13 @@ def secondary(dev, peak):
     qs = torch.rand((20, 11), generator=g, device=dev) * 150 - 50
     zs, zr = torch.randn(n, generator=g, device=dev), torch.randn(n, generator=g, device=dev)
     ac = torch.randint(0, 11, (n,), generator=g, device=dev, dtype=torch.int32)
-    ms = timed(lambda: dc.sample_returns(qs, zs, ac, zr), 50)
+    o_idx, o_R = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.float32, device=dev)
+    ms = timed(lambda: dc.sample_returns(qs, zs, ac, zr, out=(o_idx, o_R)), 50)
     out["sample_returns"] = {"rows": n, "ms": ms, "rows_per_s": n / (ms * 1e-3), "achieved_GBs": n * 20 / (ms * 1e-3) / 1e9,
                              "frac": n * 20 / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_row": 20,
-                             "note": "12 B read (z_state, z_ret, act) + 8 B written (idx, R); includes two torch.empty per call"}
-    ms = timed(lambda: dc.sample_returns_philox(qs, n, 7), 50)
+                             "note": "12 B read (z_state, z_ret, act) + 8 B written (idx, R); caller-held outputs"}
+    o_act = torch.empty(n, dtype=torch.int32, device=dev)
+    ms = timed(lambda: dc.sample_returns_philox(qs, n, 7, out=(o_idx, o_act, o_R)), 50)
     out["sample_returns_philox"] = {"rows": n, "ms": ms, "rows_per_s": n / (ms * 1e-3),
                                     "achieved_GBs": n * 12 / (ms * 1e-3) / 1e9, "frac": n * 12 / (ms * 1e-3) / 1e9 / peak,
                                     "algorithmic_bytes_per_row": 12}
@@ -480,7 +482,7 @@ def config4_leg(dev, rank, world, peak, args):
     results = {}
     for Q in (1, 64):
         q = q64[:Q].contiguous()
-        run = ddist.ShardedBoxQuery(buf, Q, C4_ACTIONS)
+        run = ddist.ShardedBoxQuery(buf, Q, C4_ACTIONS, graph=True)
         reps = 50 if Q == 1 else 10
         run(q); run(q)
         ddist.barrier()
@@ -498,7 +500,7 @@ def config4_leg(dev, rank, world, peak, args):
         results[Q] = (mom.clone(), pick.clone())
         out[f"Q{Q}"] = {"ms_per_query_pass": ms, "queries_per_s": Q / (ms * 1e-3), "rows_per_s": C4_ROWS / (ms * 1e-3),
                         "achieved_GBs": gbs, "frac_of_aggregate_peak": gbs / (peak * world),
-                        "matched_rows": float(mom[:, :, 0].sum()), "path": run.path}
+                        "matched_rows": float(mom[:, :, 0].sum()), "path": run.path + " (CUDA-graph replay)"}
     # parity: the oracle on this rank's rows, partial moments summed over ranks like the device's
     cores = max(1, _cores() // world)
     t0 = time.perf_counter()

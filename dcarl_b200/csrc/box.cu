@@ -25,50 +25,61 @@
 namespace dcarl {
 
 constexpr int kTileRows = 256;
-constexpr int kStages = 4;
+constexpr int kStages = 4;       // plain scan (HBM bound: deep ring)
 constexpr int kMaxSmemBins = 1024;  // (query, action) bins kept in shared memory: 24 KB
 
-// Largest float32 s_hi and smallest float32 s_lo with  fl64(s - w) <= q <= fl64(s + w)  <=>  s_lo <= s <= s_hi
+// Largest stored value s_hi and smallest stored value s_lo (in the buffer's element type BT) with
+//   fl64(s - w) <= q <= fl64(s + w)  <=>  s_lo <= s <= s_hi
 // (exact float64 predicate, +-1 ulp walk around the rounded candidates); an empty interval for NaN inputs.
-__device__ __forceinline__ void box_thresholds(double q, double w, float &l, float &h) {
-    h = -CUDART_INF_F; l = CUDART_INF_F;
+__device__ __forceinline__ float next_up(float x) { return nextafterf(x, CUDART_INF_F); }
+__device__ __forceinline__ float next_dn(float x) { return nextafterf(x, -CUDART_INF_F); }
+__device__ __forceinline__ double next_up(double x) { return nextafter(x, CUDART_INF); }
+__device__ __forceinline__ double next_dn(double x) { return nextafter(x, -CUDART_INF); }
+__device__ __forceinline__ void round_dn_up(double v, float &dn, float &up) { dn = __double2float_rd(v); up = __double2float_ru(v); }
+__device__ __forceinline__ void round_dn_up(double v, double &dn, double &up) { dn = v; up = v; }
+
+template <typename BT>
+__device__ __forceinline__ void box_thresholds(double q, double w, BT &l, BT &h) {
+    h = (BT)-CUDART_INF; l = (BT)CUDART_INF;
     if (q == q && w == w) {
-        // hi: largest float s with (double)s - w <= q
-        float c = __double2float_rd(q + w);
+        BT c, unused;
+        // hi: largest s with (double)s - w <= q
+        round_dn_up(q + w, c, unused);
         for (int it = 0; it < 4; ++it) {
-            const float up = nextafterf(c, CUDART_INF_F);
+            const BT up = next_up(c);
             if (up != c && (double)up - w <= q) c = up; else break;
         }
-        for (int it = 0; it < 4 && !((double)c - w <= q); ++it) c = nextafterf(c, -CUDART_INF_F);
+        for (int it = 0; it < 4 && !((double)c - w <= q); ++it) c = next_dn(c);
         if ((double)c - w <= q) h = c;
-        // lo: smallest float s with q <= (double)s + w
-        c = __double2float_ru(q - w);
+        // lo: smallest s with q <= (double)s + w
+        round_dn_up(q - w, unused, c);
         for (int it = 0; it < 4; ++it) {
-            const float dn = nextafterf(c, -CUDART_INF_F);
+            const BT dn = next_dn(c);
             if (dn != c && q <= (double)dn + w) c = dn; else break;
         }
-        for (int it = 0; it < 4 && !(q <= (double)c + w); ++it) c = nextafterf(c, CUDART_INF_F);
+        for (int it = 0; it < 4 && !(q <= (double)c + w); ++it) c = next_up(c);
         if (q <= (double)c + w) l = c;
     }
 }
 
-// thresholds layout in the workspace: lo[Q][D], hi[Q][D] (float32)
+// thresholds layout in the workspace: lo[Q][D], hi[Q][D] (element type BT)
+template <typename BT>
 __global__ void k_box_prepare(const double *__restrict__ queries, const double *__restrict__ dist, int Q,
-                              int D, float *__restrict__ lo, float *__restrict__ hi) {
+                              int D, BT *__restrict__ lo, BT *__restrict__ hi) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Q * D) return;
-    float l, h;
-    box_thresholds(queries[i], dist[i % D], l, h);
+    BT l, h;
+    box_thresholds<BT>(queries[i], dist[i % D], l, h);
     lo[i] = l;
     hi[i] = h;
 }
 
 struct BoxArgs {
-    const float *buf_state;
-    const float *buf_ret;
+    const void *buf_state;     // [M, D+1] float32, or float64 in the reference-parity storage mode
+    const void *buf_ret;       // [M]
     long long M;
     int D, Q, n_actions;
-    const float *lo, *hi;
+    const void *lo, *hi;       // [Q, D] thresholds in the buffer's element type (unfused path)
     const double *dist;  // [D+1]; dist[D] is the action tolerance
     double *out;  // [Q, n_actions, 3]; the accumulator (zero on entry) in the fused query
     int bins_in_smem;
@@ -132,25 +143,127 @@ __device__ __forceinline__ void box_select_one(const double *m, int n_actions, c
     if (out_action) *out_action = pick;
 }
 
-template <int DT, bool FUSED>
+// Fused epilogue of a scan launch (all threads of every CTA call it after their bins reached p.out): the last
+// CTA to arrive owns the totals — it moves them to out_moments (leaving the accumulator and the ticket zeroed
+// for the next call), adds the other ranks' totals through peer memory, and evaluates (mean, var) and the
+// act_test pick.
+__device__ __forceinline__ void box_epilogue(const BoxArgs &p, const int tid, const int nthr) {
+    const int nbins = p.Q * p.n_actions;
+    // ---- fused epilogue: the last CTA to arrive owns the totals
+    __shared__ unsigned s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1u) return;
+    __threadfence();
+    // totals of this GPU -> out_moments; the accumulator and the ticket are left zeroed for the next call
+    // (one CTA moves up to 400 KB here: eight independent loads in flight per thread, L2 latency each)
+    {
+        double *__restrict__ acc = p.out;
+        double *__restrict__ tot = p.out_moments;
+        const int n3 = nbins * 3;
+        for (int i0 = 0; i0 < n3; i0 += nthr * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u * nthr + tid; v[u] = i < n3 ? __ldcg(acc + i) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * nthr + tid;
+                if (i < n3) { acc[i] = 0.0; tot[i] = v[u]; }
+            }
+        }
+    }
+    if (tid == 0) *p.ticket = 0u;
+    __syncthreads();
+    if (p.peers.world > 1) peer_allreduce_cta(p.out_moments, p.out_moments, nbins * 3, p.peers);
+    __syncthreads();
+    // (mean, var) of every (query, action) pair and the act_test pick, one pair per thread and round (no
+    // barrier per query: with 64 queries a per-query loop in this one CTA took longer than the scan).  The pick
+    // is the smallest action index that passes the gate and the z-test (RLS.py:135-154): an atomic min.
+    if (p.out_action)
+        for (int q = tid; q < p.Q; q += nthr) p.out_action[q] = 0x7fffffff;
+    __syncthreads();
+    {
+        const double *mom = p.out_moments;   // (written above by this CTA: plain loads, no read-only path)
+        double *mv = p.out_mv;
+        for (int i0 = 0; i0 < nbins; i0 += nthr * 4) {
+            double n_[4], s1_[4], s2_[4], n0_[4], r1_[4], r2_[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                       // all loads of four pairs first
+                const int i = min(i0 + u * nthr + tid, nbins - 1);
+                const int q = i / p.n_actions;
+                n_[u] = mom[(size_t)i * 3]; s1_[u] = mom[(size_t)i * 3 + 1]; s2_[u] = mom[(size_t)i * 3 + 2];
+                const double *m0 = mom + (size_t)q * p.n_actions * 3;
+                n0_[u] = m0[0]; r1_[u] = m0[1]; r2_[u] = m0[2];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nthr + tid;
+                if (i >= nbins) continue;
+                const int q = i / p.n_actions, a = i - q * p.n_actions;
+                const double n0 = n0_[u];
+                const double mean0 = n0 > 0.0 ? r1_[u] / n0 : -1.0;
+                const double var0 = n0 > 0.0 ? fmax(r2_[u] / n0 - mean0 * mean0, 0.0) : -1.0;
+                const double n = n_[u];
+                double mean = -1.0, var = -1.0;                                    // RLS.py:169-170
+                if (n > 0.0) { mean = s1_[u] / n; var = fmax(s2_[u] / n - mean * mean, 0.0); }
+                if (mv) { mv[(size_t)i * 2] = mean; mv[(size_t)i * 2 + 1] = var; }
+                if (!p.out_action || a == 0 || n0 < (double)p.rp.visited_times_thres ||
+                    n < (double)p.rp.min_candidate_visits || mean0 > p.rp.rule_mean_gate)
+                    continue;                                                      // RLS.py:141
+                const double z = (mean - mean0) / sqrt(var0 / n0 + var / n);     // RLS.py:144-148
+                if (0.5 * erfc(-z * 0.70710678118654752440) > p.rp.confidence_thres) atomicMin(p.out_action + q, a);   // RLS.py:150-154
+            }
+        }
+    }
+    __syncthreads();
+    if (p.out_action)
+        for (int q = tid; q < p.Q; q += nthr)
+            if (__ldcg(p.out_action + q) == 0x7fffffff) p.out_action[q] = 0;
+}
+
+// ---- many queries: a per-dimension bitmap pre-filter ---------------------------------------------------
+// With Q queries the plain loop spends ~60 instructions per (warp, query) on the 20-dim test and is issue
+// bound long before HBM (Q = 64: 6 % of the HBM roofline).  The filter makes the cost per row independent
+// of Q: every observation dim is cut into kSigBins bins over the range the queries' boxes span, and a table
+// holds, per (dim, bin), the 64-bit set of queries whose interval [s_lo, s_hi] overlaps the bin.  The bin
+// function is monotone in the stored value, so a row inside a query's box always falls into a bin that has
+// the query's bit: the AND of the row's 20 table entries is a superset of its matching queries (a handful of
+// instructions per dim for all queries at once, the warp leaves as soon as no lane has a candidate left), and
+// the few (row, query) pairs that survive take the exact test as before.  Rows outside the queries' range
+// clamp into the edge bins (conservative); NaN coordinates land in bin 0 and fail the exact test.
+constexpr int kSigBins = 32, kSigMaxQ = 64;
+__host__ __device__ inline size_t filter_smem_bytes(int Q, int D) {
+    return (size_t)D * kSigBins * sizeof(unsigned long long) + (size_t)D * sizeof(float2) + (size_t)2 * Q * D;
+}
+__device__ __forceinline__ int sig_bin(float x, float2 g) {
+    const int b = __float2int_rd(fmaf(x, g.x, g.y));       // NaN -> 0, saturating
+    return max(0, min(b, kSigBins - 1));
+}
+
+template <typename BT, int DT, bool FUSED>
 __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int D = DT > 0 ? DT : p.D;
     const int W = D + 1;
     const int tid = threadIdx.x;
-    const size_t tile_bytes = (size_t)kTileRows * W * sizeof(float);
-    const size_t ret_bytes = (size_t)kTileRows * sizeof(float);
-    // layout: [stages x state tile][stages x ret tile][lo Q*D][hi Q*D][bins][mbarriers]
-    float *st_tile = reinterpret_cast<float *>(smem_raw);
-    float *rt_tile = reinterpret_cast<float *>(smem_raw + kStages * tile_bytes);
-    float *slo = rt_tile + kStages * kTileRows;
-    float *shi = slo + p.Q * D;
-    size_t off = kStages * (tile_bytes + ret_bytes) + (size_t)2 * p.Q * D * sizeof(float);
+    constexpr int NS = kStages;
+    const size_t tile_bytes = (size_t)kTileRows * W * sizeof(BT);
+    const size_t ret_bytes = (size_t)kTileRows * sizeof(BT);
+    // layout: [stages x state tile][stages x ret tile][lo Q*D][hi Q*D][head][bins][mbarriers]
+    BT *st_tile = reinterpret_cast<BT *>(smem_raw);
+    BT *rt_tile = reinterpret_cast<BT *>(smem_raw + NS * tile_bytes);
+    BT *slo = rt_tile + NS * kTileRows;
+    BT *shi = slo + p.Q * D;
+    size_t off = NS * (tile_bytes + ret_bytes) + (size_t)2 * p.Q * D * sizeof(BT);
     off = (off + 15) & ~(size_t)15;
     // head thresholds {lo0, hi0, lo1, hi1 | lo2, hi2, lo3, hi3} per query: two 16-byte broadcast loads
-    // per (warp, query) instead of eight 4-byte ones (with many queries the scan is bound by them)
+    // per (warp, query) instead of eight 4-byte ones (float32 buffers)
+    constexpr bool HEAD = DT >= 4 && sizeof(BT) == 4;
     float4 *shead = reinterpret_cast<float4 *>(smem_raw + off);
     off += (size_t)p.Q * 2 * sizeof(float4);
+    off = (off + 15) & ~(size_t)15;
     double *sbins = reinterpret_cast<double *>(smem_raw + off);
     const int nbins = p.Q * p.n_actions;
     off += p.bins_in_smem ? (size_t)nbins * 3 * sizeof(double) : 0;
@@ -158,39 +271,40 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
 
     if (FUSED) {
         // every CTA derives the thresholds of its queries itself (Q*D of them: trivial next to a tile)
-        for (int i = tid; i < p.Q * D; i += kTileRows) box_thresholds(p.queries[i], p.dist[i % D], slo[i], shi[i]);
-        __syncthreads();
+        for (int i = tid; i < p.Q * D; i += kTileRows) box_thresholds<BT>(p.queries[i], p.dist[i % D], slo[i], shi[i]);
     } else {
-        for (int i = tid; i < p.Q * D; i += kTileRows) { slo[i] = p.lo[i]; shi[i] = p.hi[i]; }
+        const BT *glo = reinterpret_cast<const BT *>(p.lo), *ghi = reinterpret_cast<const BT *>(p.hi);
+        for (int i = tid; i < p.Q * D; i += kTileRows) { slo[i] = glo[i]; shi[i] = ghi[i]; }
     }
-    if (DT >= 4) {
-        if (!FUSED) __syncthreads();
+    __syncthreads();
+    if (HEAD)
         for (int q = tid; q < p.Q; q += kTileRows) {
-            const float *l = slo + (size_t)q * D, *h = shi + (size_t)q * D;
-            shead[2 * q] = make_float4(l[0], h[0], l[1], h[1]);
-            shead[2 * q + 1] = make_float4(l[2], h[2], l[3], h[3]);
+            const BT *l = slo + (size_t)q * D, *h = shi + (size_t)q * D;
+            shead[2 * q] = make_float4((float)l[0], (float)h[0], (float)l[1], (float)h[1]);
+            shead[2 * q + 1] = make_float4((float)l[2], (float)h[2], (float)l[3], (float)h[3]);
         }
-    }
     if (p.bins_in_smem)
         for (int i = tid; i < nbins * 3; i += kTileRows) sbins[i] = 0.0;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
     __syncthreads();
 
+    const BT *gstate = reinterpret_cast<const BT *>(p.buf_state);
+    const BT *gret = reinterpret_cast<const BT *>(p.buf_ret);
     const long long n_tiles = (p.M + kTileRows - 1) / kTileRows;
     const long long n_full = p.M / kTileRows;  // tiles that are complete (TMA-loadable)
     auto issue = [&](long long tile, int stage) {
         // thread 0 only; complete tiles only
         mbar_arrive_expect_tx(&full[stage], (unsigned)(tile_bytes + ret_bytes));
-        tma_load_1d(st_tile + (size_t)stage * kTileRows * W, p.buf_state + tile * kTileRows * W,
+        tma_load_1d(st_tile + (size_t)stage * kTileRows * W, gstate + tile * kTileRows * W,
                     (unsigned)tile_bytes, &full[stage]);
-        tma_load_1d(rt_tile + (size_t)stage * kTileRows, p.buf_ret + tile * kTileRows, (unsigned)ret_bytes,
+        tma_load_1d(rt_tile + (size_t)stage * kTileRows, gret + tile * kTileRows, (unsigned)ret_bytes,
                     &full[stage]);
     };
     if (tid == 0)
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < NS; ++s) {
             const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
             if (t < n_full) issue(t, s);
         }
@@ -199,48 +313,46 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
     const double dist_act = p.dist[D];
     long long it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int stage = (int)(it % kStages);
-        float *ts = st_tile + (size_t)stage * kTileRows * W;
-        float *tr = rt_tile + (size_t)stage * kTileRows;
+        const int stage = (int)(it % NS);
+        BT *ts = st_tile + (size_t)stage * kTileRows * W;
+        BT *tr = rt_tile + (size_t)stage * kTileRows;
         if (tile < n_full) {
-            mbar_wait(&full[stage], (unsigned)((it / kStages) & 1));
+            mbar_wait(&full[stage], (unsigned)((it / NS) & 1));
         } else {
             // ragged last tile: plain cooperative loads
             const long long base = tile * kTileRows;
             const int rows = (int)(p.M - base);
-            for (int i = tid; i < rows * W; i += kTileRows) ts[i] = p.buf_state[base * W + i];
-            if (tid < rows) tr[tid] = p.buf_ret[base + tid];
+            for (int i = tid; i < rows * W; i += kTileRows) ts[i] = gstate[base * W + i];
+            if (tid < rows) tr[tid] = gret[base + tid];
             __syncthreads();
         }
         const long long row = tile * kTileRows + tid;
         const bool in_buf = row < p.M;
-        const float *x = ts + (size_t)tid * W;
-        float xr[DT > 0 ? DT : 1];
+        const BT *x = ts + (size_t)tid * W;
+        BT xr[DT > 0 ? DT : 1];
         if (DT > 0) {
 #pragma unroll
             for (int d = 0; d < DT; ++d) xr[d] = x[d];
         }
-        for (int q = 0; q < p.Q; ++q) {
-            const float *l = slo + q * D, *h = shi + q * D;
-            bool ok = in_buf;
+        // the exact test of query q for this thread's row, and the accumulation of the warp's hits
+        auto exact_query = [&](int q, bool pre) {
+            const BT *l = slo + q * D, *h = shi + q * D;
+            bool ok = pre;
             if (DT > 0) {
-                constexpr int kHead = DT < 4 ? DT : 4;
-                if (DT >= 4) {
+                constexpr int kHead = HEAD ? 4 : 0;
+                if (HEAD) {
                     const float4 t0 = shead[2 * q], t1 = shead[2 * q + 1];
-                    ok = ok & (xr[0] >= t0.x) & (xr[0] <= t0.y) & (xr[1] >= t0.z) & (xr[1] <= t0.w) &
-                         (xr[2] >= t1.x) & (xr[2] <= t1.y) & (xr[3] >= t1.z) & (xr[3] <= t1.w);
-                } else {
-#pragma unroll
-                    for (int d = 0; d < kHead; ++d) ok = ok && (xr[d] >= l[d]) && (xr[d] <= h[d]);
+                    ok = ok & ((float)xr[0] >= t0.x) & ((float)xr[0] <= t0.y) & ((float)xr[1] >= t0.z) & ((float)xr[1] <= t0.w) &
+                         ((float)xr[2] >= t1.x) & ((float)xr[2] <= t1.y) & ((float)xr[3] >= t1.z) & ((float)xr[3] <= t1.w);
+                    // with many queries most (row, query) pairs die on the first dims: leave before the rest
+                    if (p.Q > 1 && !__any_sync(FULL_MASK, ok)) return;
                 }
-                // with many queries most (row, query) pairs die on the first dims: leave before the rest
-                if (p.Q > 1 && !__any_sync(FULL_MASK, ok)) continue;
 #pragma unroll
                 for (int d = kHead; d < DT; ++d) ok = ok && (xr[d] >= l[d]) && (xr[d] <= h[d]);
             } else {
-                for (int d = 0; d < D; ++d) { const float v = x[d]; ok = ok && (v >= l[d]) && (v <= h[d]); }
+                for (int d = 0; d < D; ++d) { const BT v = x[d]; ok = ok && (v >= l[d]) && (v <= h[d]); }
             }
-            if (!__any_sync(FULL_MASK, ok)) continue;
+            if (!__any_sync(FULL_MASK, ok)) return;
             // the stored action picks the candidate(s): s_act - dist <= a <= s_act + dist in float64
             const double sa = ok ? (double)x[D] : 0.0;
             const double alo = sa - dist_act, ahi = sa + dist_act;
@@ -257,12 +369,11 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
                 if (p.bins_in_smem) warp_accumulate<true>(hit, q * p.n_actions + a, r, bins);
                 else warp_accumulate<false>(hit, q * p.n_actions + a, r, bins);
             }
-        }
+        };
+        for (int q = 0; q < p.Q; ++q) exact_query(q, in_buf);
+        const long long nt = tile + (long long)NS * gridDim.x;
         __syncthreads();  // everyone is done with this stage
-        if (tid == 0) {
-            const long long nt = tile + (long long)kStages * gridDim.x;
-            if (nt < n_full) issue(nt, stage);
-        }
+        if (tid == 0 && nt < n_full) issue(nt, stage);
     }
     if (p.bins_in_smem) {
         __syncthreads();
@@ -271,29 +382,187 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
             if (v != 0.0) atomicAdd(p.out + i, v);
         }
     }
-    if (!FUSED) return;
-    // ---- fused epilogue: the last CTA to arrive owns the totals
-    __shared__ unsigned s_ticket;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
-    // totals of this GPU -> out_moments; the accumulator and the ticket are left zeroed for the next call
-    for (int i = tid; i < nbins * 3; i += kTileRows) {
-        const double v = __ldcg(p.out + i);
-        p.out[i] = 0.0;
-        p.out_moments[i] = v;
+    if (FUSED) box_epilogue(p, tid, kTileRows);
+}
+
+// ---- many queries (float32 buffer, 20 observation dims): the bitmap-filtered scan ----------------------------
+// Work per row is uneven here (a row near a query takes all 20 table lookups and the exact test, most rows leave
+// after 8-12 dims), so there is no CTA-wide tile and no CTA barrier in the loop: every WARP streams its own
+// sub-tiles of 32 rows through a private ring (1-D TMA bulk copies of 32 x 84 + 32 x 4 bytes, one mbarrier per
+// stage, lane 0 issues, the 32 lanes wait), warp w of the grid taking sub-tiles w, w + n_warps, ...
+constexpr int kFiltWarps = 8, kFiltStages = 3, kFiltD = 20, kFiltW = kFiltD + 1;
+constexpr int kFiltStageBytes = 32 * kFiltW * 4 + 32 * 4;   // 2816: state rows, then the returns
+
+__host__ __device__ inline size_t box_filter_smem_bytes(int Q, int n_actions, bool bins_in_smem) {
+    size_t off = (size_t)kFiltWarps * kFiltStages * kFiltStageBytes + (size_t)2 * Q * kFiltD * sizeof(float);
+    off = (off + 15) & ~(size_t)15;
+    off += filter_smem_bytes(Q, kFiltD);
+    off = (off + 15) & ~(size_t)15;
+    if (bins_in_smem) off += (size_t)Q * n_actions * 3 * sizeof(double);
+    off += (size_t)kFiltWarps * kFiltStages * sizeof(uint64_t);
+    return off;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int D = kFiltD, W = kFiltW, NT = kFiltWarps * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // layout: [warps x stages x {32 rows, 32 returns}][lo Q*D][hi Q*D][tables][bins][mbarriers]
+    unsigned char *ring = smem_raw + (size_t)warp * kFiltStages * kFiltStageBytes;
+    float *slo = reinterpret_cast<float *>(smem_raw + (size_t)kFiltWarps * kFiltStages * kFiltStageBytes);
+    float *shi = slo + p.Q * D;
+    size_t off = (size_t)kFiltWarps * kFiltStages * kFiltStageBytes + (size_t)2 * p.Q * D * sizeof(float);
+    off = (off + 15) & ~(size_t)15;
+    // per (dim, bin) the set of queries whose interval overlaps the bin; per dim {scale, offset} of the bin
+    // function; scratch: the first / last bin of every (query, dim) interval
+    unsigned long long *stab = reinterpret_cast<unsigned long long *>(smem_raw + off);
+    float2 *sgeo = reinterpret_cast<float2 *>(stab + D * kSigBins);
+    unsigned char *sb01 = reinterpret_cast<unsigned char *>(sgeo + D);
+    off += filter_smem_bytes(p.Q, D);
+    off = (off + 15) & ~(size_t)15;
+    double *sbins = reinterpret_cast<double *>(smem_raw + off);
+    const int nbins = p.Q * p.n_actions;
+    off += p.bins_in_smem ? (size_t)nbins * 3 * sizeof(double) : 0;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + off) + warp * kFiltStages;
+
+    if (FUSED) {
+        for (int i = tid; i < p.Q * D; i += NT) box_thresholds<float>(p.queries[i], p.dist[i % D], slo[i], shi[i]);
+    } else {
+        const float *glo = reinterpret_cast<const float *>(p.lo), *ghi = reinterpret_cast<const float *>(p.hi);
+        for (int i = tid; i < p.Q * D; i += NT) { slo[i] = glo[i]; shi[i] = ghi[i]; }
     }
-    if (tid == 0) *p.ticket = 0u;
+    if (lane == 0) {
+        for (int s = 0; s < kFiltStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
-    if (p.peers.world > 1) peer_allreduce_cta(p.out_moments, p.out_moments, nbins * 3, p.peers);
+    // this warp's first sub-tiles are on their way while the CTA builds the tables
+    const float *gstate = reinterpret_cast<const float *>(p.buf_state);
+    const float *gret = reinterpret_cast<const float *>(p.buf_ret);
+    const long long n_sub = p.M / 32;                       // complete sub-tiles (TMA-loadable)
+    const long long n_warps = (long long)gridDim.x * kFiltWarps;
+    const long long w0 = (long long)blockIdx.x * kFiltWarps + warp;
+    auto issue = [&](long long sub, int stage) {            // lane 0 only
+        unsigned char *dst = ring + (size_t)stage * kFiltStageBytes;
+        mbar_arrive_expect_tx(&full[stage], (unsigned)kFiltStageBytes);
+        tma_load_1d(dst, gstate + sub * 32 * W, 32 * W * 4, &full[stage]);
+        tma_load_1d(dst + 32 * W * 4, gret + sub * 32, 32 * 4, &full[stage]);
+    };
+    if (lane == 0)
+        for (int s = 0; s < kFiltStages; ++s) {
+            const long long t = w0 + (long long)s * n_warps;
+            if (t < n_sub) issue(t, s);
+        }
+    // bin geometry: the range of the finite thresholds of all queries, per dim
+    if (tid < D) {
+        float gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
+        for (int q = 0; q < p.Q; ++q) {
+            const float l = slo[q * D + tid], h = shi[q * D + tid];
+            if (l <= h) { gmin = fminf(gmin, l); gmax = fmaxf(gmax, h); }
+        }
+        float scale = 0.f;
+        if (gmin < gmax && gmax - gmin < CUDART_INF_F) scale = (float)kSigBins / (gmax - gmin);
+        if (!(gmin <= gmax)) { gmin = 0.f; scale = 0.f; }                    // no query has an interval in this dim
+        sgeo[tid] = make_float2(scale, -gmin * scale);                        // bin coordinate t = fma(x, scale, offset)
+    }
     __syncthreads();
-    for (int q = tid; q < p.Q; q += kTileRows)
-        box_select_one(p.out_moments + (size_t)q * p.n_actions * 3, p.n_actions, p.rp,
-                       p.out_mv ? p.out_mv + (size_t)q * p.n_actions * 2 : nullptr,
-                       p.out_action ? p.out_action + q : nullptr);
+    // first / last bin of every interval (the same bin function as the rows': monotone in the stored value,
+    // so a value inside [l, h] lands in [bin(l), bin(h)]); an empty interval gets first > last
+    for (int i = tid; i < p.Q * D; i += NT) {
+        const float l = slo[i], h = shi[i];
+        const float2 g = sgeo[i % D];
+        const bool some = l <= h;
+        sb01[2 * i] = (unsigned char)(some ? sig_bin(l, g) : 1);
+        sb01[2 * i + 1] = (unsigned char)(some ? sig_bin(h, g) : 0);
+    }
+    __syncthreads();
+    for (int e = tid; e < D * kSigBins; e += NT) {
+        const int d = e / kSigBins, b = e % kSigBins;
+        unsigned long long m = 0ull;
+        for (int q = 0; q < p.Q; ++q) {
+            const int i = q * D + d;
+            m |= (unsigned long long)((int)sb01[2 * i] <= b && b <= (int)sb01[2 * i + 1]) << q;
+        }
+        stab[e] = m;
+    }
+    if (p.bins_in_smem)
+        for (int i = tid; i < nbins * 3; i += NT) sbins[i] = 0.0;
+    __syncthreads();
+
+    double *bins = p.bins_in_smem ? sbins : p.out;
+    const double dist_act = p.dist[D];
+    // One row per lane: x = its 20 observation values + the action (shared or global memory), r = its return.
+    auto scan_row = [&](const float *x, const float *r, bool valid) {
+        // candidates: the AND of the row's table entries, all queries at once, four dims per round; the warp
+        // leaves as soon as no lane has a candidate left (most rows are out after two or three rounds)
+        unsigned long long surv = valid ? ~0ull : 0ull;
+        bool alive = true;                                  // warp-uniform
+#pragma unroll
+        for (int g = 0; g < D / 4; ++g) {
+            if (alive) {
+                unsigned long long m[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int d = 4 * g + u;
+                    m[u] = stab[d * kSigBins + sig_bin(x[d], sgeo[d])];
+                }
+                surv &= (m[0] & m[1]) & (m[2] & m[3]);
+                alive = __any_sync(FULL_MASK, surv != 0ull);
+            }
+        }
+        if (!alive) return;
+        // the few surviving (row, query) pairs take the exact test, each lane on its own pairs: hits are
+        // rare with many queries, so they go to the bins one atomic triple at a time
+        while (surv) {
+            const int q = __ffsll((long long)surv) - 1;
+            surv &= surv - 1ull;
+            const float *l = slo + q * D, *h = shi + q * D;
+            bool ok = true;
+#pragma unroll 4
+            for (int d = 0; d < D; ++d) { const float v = x[d]; ok = ok && (v >= l[d]) && (v <= h[d]); }
+            if (!ok) continue;
+            // the stored action picks the candidate(s): s_act - dist <= a <= s_act + dist in float64
+            const double sa = (double)x[D];
+            const double alo = sa - dist_act, ahi = sa + dist_act;
+            if (!(alo == alo) || !(ahi == ahi)) continue;
+            const int a0 = (int)fmax(ceil(alo), 0.0), a1 = (int)fmin(floor(ahi), (double)(p.n_actions - 1));
+            const double rr = (double)*r;
+            for (int a = a0; a <= a1; ++a)
+                if (alo <= (double)a && (double)a <= ahi) {
+                    double *b = bins + ((size_t)q * p.n_actions + a) * 3;
+                    atomicAdd(b + 0, 1.0);
+                    atomicAdd(b + 1, rr);
+                    atomicAdd(b + 2, rr * rr);
+                }
+        }
+    };
+
+    long long it = 0;
+    for (long long sub = w0; sub < n_sub; sub += n_warps, ++it) {
+        const int stage = (int)(it % kFiltStages);
+        const float *ts = reinterpret_cast<const float *>(ring + (size_t)stage * kFiltStageBytes);
+        mbar_wait(&full[stage], (unsigned)((it / kFiltStages) & 1));
+        scan_row(ts + lane * W, ts + 32 * W + lane, true);
+        __syncwarp();                                       // every lane is done with the stage
+        const long long nt = sub + (long long)kFiltStages * n_warps;
+        if (lane == 0 && nt < n_sub) issue(nt, stage);
+    }
+    // the last M % 32 rows, straight from global memory, by the warp whose turn it would be
+    if ((p.M & 31) != 0 && w0 == n_sub % n_warps) {
+        const long long row = n_sub * 32 + lane;
+        const bool valid = row < p.M;
+        const long long rr = valid ? row : p.M - 1;
+        scan_row(gstate + rr * W, gret + rr, valid);
+    }
+    if (p.bins_in_smem) {
+        __syncthreads();
+        for (int i = tid; i < nbins * 3; i += NT) {
+            const double v = sbins[i];
+            if (v != 0.0) atomicAdd(p.out + i, v);
+        }
+    }
+    if (FUSED) box_epilogue(p, tid, NT);
 }
 
 // moments -> mean/var (+ sentinel) and the act_test pick, one thread per query
@@ -305,14 +574,73 @@ __global__ void k_box_select(const double *__restrict__ mom, int Q, int n_action
                    out_mv ? out_mv + (size_t)q * n_actions * 2 : nullptr, out_action ? out_action + q : nullptr);
 }
 
-static size_t box_smem_bytes(int Q, int D, int n_actions, bool bins_in_smem) {
+static size_t box_smem_bytes(int Q, int D, int n_actions, bool bins_in_smem, size_t elem = sizeof(float)) {
     const int W = D + 1;
-    size_t off = (size_t)kStages * kTileRows * (W + 1) * sizeof(float) + (size_t)2 * Q * D * sizeof(float);
+    size_t off = (size_t)kStages * kTileRows * (W + 1) * elem + (size_t)2 * Q * D * elem;
     off = (off + 15) & ~(size_t)15;
     off += (size_t)Q * 32;   // head thresholds
+    off = (off + 15) & ~(size_t)15;
     if (bins_in_smem) off += (size_t)Q * n_actions * 3 * sizeof(double);
     off += kStages * sizeof(uint64_t);
     return off;
+}
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+struct ScanPlan {
+    int qc;             // queries per launch
+    bool filt;          // launches of >= 8 queries take the bitmap-filtered kernel
+    size_t elem;
+};
+// Queries are processed in chunks whose thresholds (+ bins) fit beside the tile ring; many queries on a
+// float32 buffer of 20 observation dims go through the bitmap filter, at most kSigMaxQ per launch.
+static int plan_scan(int Q, int D, int n_actions, int buf_is_f64, ScanPlan &sp) {
+    sp.elem = buf_is_f64 ? sizeof(double) : sizeof(float);
+    sp.filt = !buf_is_f64 && D == kFiltD && Q >= 8;
+    sp.qc = Q;
+    if (sp.filt) {
+        if (sp.qc > kSigMaxQ) sp.qc = kSigMaxQ;
+        return 0;                                           // 64 queries always fit (box_filter_smem_bytes: 86 KB)
+    }
+    while (sp.qc > 1 && box_smem_bytes(sp.qc, D, n_actions, false, sp.elem) > kSmemBudget) sp.qc = (sp.qc + 1) / 2;
+    if (box_smem_bytes(sp.qc, D, n_actions, false, sp.elem) > kSmemBudget) return bad_arg(4, "D too large for the tile ring");
+    return 0;
+}
+
+// One scan launch of qn queries (a.Q etc. filled by the caller; unfused: thresholds from the workspace; fused:
+// computed in the kernel, epilogue on).  Persistent grid: CTAs per SM by shared memory.
+template <typename BT, bool FUSED>
+static int launch_scan(BoxArgs &a, const ScanPlan &sp, int sms, cudaStream_t st) {
+    const int qn = a.Q, D = a.D, na = a.n_actions;
+    auto grid_of = [&](size_t smem, long long units) {
+        int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));   // 228 KB per SM, 1 KB of it reserved per resident CTA
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        long long grid = (long long)sms * per_sm;
+        if (grid > units) grid = units;
+        return (unsigned)(grid < 1 ? 1 : grid);             // (an empty shard still takes part in the reduction)
+    };
+    if constexpr (sizeof(BT) == 4) {
+        if (sp.filt && qn >= 8) {
+            a.bins_in_smem = (qn * na <= kMaxSmemBins) && box_filter_smem_bytes(qn, na, true) <= kSmemBudget;
+            const size_t smem = box_filter_smem_bytes(qn, na, a.bins_in_smem);
+            const unsigned grid = grid_of(smem, (a.M / 32 + kFiltWarps - 1) / kFiltWarps);
+            DCARL_CUDA(cudaFuncSetAttribute(k_box_filter<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_box_filter<FUSED><<<grid, kFiltWarps * 32, smem, st>>>(a);
+            DCARL_LAUNCH_CHECK("k_box_filter");
+            return 0;
+        }
+    }
+    a.bins_in_smem = (qn * na <= kMaxSmemBins) && box_smem_bytes(qn, D, na, true, sp.elem) <= kSmemBudget;
+    const size_t smem = box_smem_bytes(qn, D, na, a.bins_in_smem, sp.elem);
+    const unsigned grid = grid_of(smem, (a.M + kTileRows - 1) / kTileRows);
+    auto go = [&](auto kern) -> int {
+        DCARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTileRows, smem, st>>>(a);
+        DCARL_LAUNCH_CHECK("k_box_moments");
+        return 0;
+    };
+    if (D == 20) return go(k_box_moments<BT, 20, FUSED>);
+    return go(k_box_moments<BT, 0, FUSED>);
 }
 
 }  // namespace dcarl
@@ -322,61 +650,48 @@ using namespace dcarl;
 extern "C" size_t dcarl_box_moments_ws(int32_t Q, int32_t D, int32_t n_actions) {
     (void)n_actions;
     if (Q <= 0 || D <= 0) return 0;
-    return (size_t)2 * Q * D * sizeof(float);
+    return (size_t)2 * Q * D * sizeof(double);   // thresholds in the widest element type
 }
 
-extern "C" int dcarl_box_moments(const float *buf_state, const float *buf_ret, int64_t M, int32_t D,
+extern "C" int dcarl_box_moments(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
                                  const double *dist, const double *queries, int32_t Q, int32_t n_actions,
                                  double *out_moments, void *ws, size_t ws_bytes, dcarl_stream_t stream) {
-    if (M < 0) return bad_arg(3, "M < 0");
-    if (D <= 0 || D > 255) return bad_arg(4, "D must be in [1, 255]");
-    if (Q < 0) return bad_arg(7, "Q < 0");
-    if (n_actions <= 0) return bad_arg(8, "n_actions <= 0");
+    if (M < 0) return bad_arg(4, "M < 0");
+    if (D <= 0 || D > 255) return bad_arg(5, "D must be in [1, 255]");
+    if (Q < 0) return bad_arg(8, "Q < 0");
+    if (n_actions <= 0) return bad_arg(9, "n_actions <= 0");
     if (Q == 0) return 0;
-    if (!dist || !queries) return bad_arg(5, "dist/queries is null");
-    if (!out_moments) return bad_arg(9, "out_moments is null");
+    if (!dist || !queries) return bad_arg(6, "dist/queries is null");
+    if (!out_moments) return bad_arg(10, "out_moments is null");
     if (M > 0 && (!buf_state || !buf_ret)) return bad_arg(1, "buffer is null");
     if (((uintptr_t)buf_state & 15) || ((uintptr_t)buf_ret & 15)) return bad_arg(1, "buffer must be 16-byte aligned");
-    if (!ws || ws_bytes < dcarl_box_moments_ws(Q, D, n_actions))
-        return bad_arg(10, "workspace too small (see dcarl_box_moments_ws)");
+    if (!ws || ws_bytes < dcarl_box_moments_ws(Q, D, n_actions) || ((uintptr_t)ws & 7))
+        return bad_arg(11, "workspace too small or misaligned (see dcarl_box_moments_ws)");
     cudaStream_t st = (cudaStream_t)stream;
     DCARL_CUDA(cudaMemsetAsync(out_moments, 0, (size_t)Q * n_actions * 3 * sizeof(double), st));
     if (M == 0) return 0;
+    ScanPlan sp;
+    if (int rc = plan_scan(Q, D, n_actions, buf_is_f64, sp)) return rc;
 
-    float *lo = reinterpret_cast<float *>(ws);
-    float *hi = lo + (size_t)Q * D;
-    k_box_prepare<<<(Q * D + 127) / 128, 128, 0, st>>>(queries, dist, Q, D, lo, hi);
+    const size_t nthr = (size_t)Q * D;
+    void *lo = ws, *hi = reinterpret_cast<unsigned char *>(ws) + nthr * sp.elem;
+    if (buf_is_f64) k_box_prepare<double><<<(Q * D + 127) / 128, 128, 0, st>>>(queries, dist, Q, D, (double *)lo, (double *)hi);
+    else k_box_prepare<float><<<(Q * D + 127) / 128, 128, 0, st>>>(queries, dist, Q, D, (float *)lo, (float *)hi);
     DCARL_LAUNCH_CHECK("k_box_prepare");
 
-    // queries are processed in chunks whose thresholds (+ bins) fit beside the tile ring
-    const size_t budget = 200 * 1024;
-    int qc = Q;
-    while (qc > 1 && box_smem_bytes(qc, D, n_actions, false) > budget) qc = (qc + 1) / 2;
-    if (box_smem_bytes(qc, D, n_actions, false) > budget) return bad_arg(4, "D too large for the tile ring");
     const int sms = sm_count();
-    const long long n_tiles = (M + kTileRows - 1) / kTileRows;
-    for (int q0 = 0; q0 < Q; q0 += qc) {
-        const int qn = (Q - q0 < qc) ? Q - q0 : qc;
+    for (int q0 = 0; q0 < Q; q0 += sp.qc) {
+        const int qn = (Q - q0 < sp.qc) ? Q - q0 : sp.qc;
         BoxArgs a;
         a.buf_state = buf_state; a.buf_ret = buf_ret; a.M = M; a.D = D; a.Q = qn; a.n_actions = n_actions;
-        a.lo = lo + (size_t)q0 * D; a.hi = hi + (size_t)q0 * D; a.dist = dist;
+        a.lo = reinterpret_cast<unsigned char *>(lo) + (size_t)q0 * D * sp.elem;
+        a.hi = reinterpret_cast<unsigned char *>(hi) + (size_t)q0 * D * sp.elem;
+        a.dist = dist;
         a.out = out_moments + (size_t)q0 * n_actions * 3;
-        a.bins_in_smem = (qn * n_actions <= kMaxSmemBins) &&
-                         box_smem_bytes(qn, D, n_actions, true) <= budget;
-        const size_t smem = box_smem_bytes(qn, D, n_actions, a.bins_in_smem);
-        int per_sm = (int)((size_t)(220 * 1024) / smem);
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;
-        long long grid = (long long)sms * per_sm;
-        if (grid > n_tiles) grid = n_tiles;
-        if (D == 20) {
-            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_box_moments<20, false><<<(unsigned)grid, kTileRows, smem, st>>>(a);
-        } else {
-            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_box_moments<0, false><<<(unsigned)grid, kTileRows, smem, st>>>(a);
-        }
-        DCARL_LAUNCH_CHECK("k_box_moments");
+        a.queries = nullptr; a.ticket = nullptr; a.out_moments = nullptr; a.out_mv = nullptr; a.out_action = nullptr;
+        a.rp = dcarl_rls_params{}; a.peers = PeerCtx{};
+        const int rc = buf_is_f64 ? launch_scan<double, false>(a, sp, sms, st) : launch_scan<float, false>(a, sp, sms, st);
+        if (rc) return rc;
     }
     return 0;
 }
@@ -387,46 +702,40 @@ extern "C" size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions) {
     return (size_t)Q * n_actions * 3 * sizeof(double) + 16;   // accumulator + ticket
 }
 
-extern "C" int dcarl_box_query(const float *buf_state, const float *buf_ret, int64_t M, int32_t D,
+extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
                                const double *dist, const double *queries, int32_t Q, int32_t n_actions,
                                const dcarl_rls_params *rp, double *out_moments, double *out_mean_var,
                                int32_t *out_action, void *ws, size_t ws_bytes, const dcarl_peer_ctx *peers,
                                dcarl_stream_t stream) {
-    if (M < 0) return bad_arg(3, "M < 0");
-    if (D <= 0 || D > 255) return bad_arg(4, "D must be in [1, 255]");
-    if (Q < 0) return bad_arg(7, "Q < 0");
-    if (n_actions <= 0) return bad_arg(8, "n_actions <= 0");
-    if (!rp) return bad_arg(9, "params is null");
+    if (M < 0) return bad_arg(4, "M < 0");
+    if (D <= 0 || D > 255) return bad_arg(5, "D must be in [1, 255]");
+    if (Q < 0) return bad_arg(8, "Q < 0");
+    if (n_actions <= 0) return bad_arg(9, "n_actions <= 0");
+    if (!rp) return bad_arg(10, "params is null");
     if (Q == 0) return 0;
-    if (!dist || !queries) return bad_arg(5, "dist/queries is null");
-    if (!out_moments) return bad_arg(10, "out_moments is null");
+    if (!dist || !queries) return bad_arg(6, "dist/queries is null");
+    if (!out_moments) return bad_arg(11, "out_moments is null");
     if (M > 0 && (!buf_state || !buf_ret)) return bad_arg(1, "buffer is null");
     if (((uintptr_t)buf_state & 15) || ((uintptr_t)buf_ret & 15)) return bad_arg(1, "buffer must be 16-byte aligned");
     if (!ws || ws_bytes < dcarl_box_query_ws(Q, D, n_actions) || ((uintptr_t)ws & 15))
-        return bad_arg(13, "workspace too small or misaligned (see dcarl_box_query_ws)");
+        return bad_arg(14, "workspace too small or misaligned (see dcarl_box_query_ws)");
     cudaStream_t st = (cudaStream_t)stream;
     double *acc = reinterpret_cast<double *>(ws);
     unsigned *ticket = reinterpret_cast<unsigned *>(acc + (size_t)Q * n_actions * 3);
-
-    const size_t budget = 200 * 1024;
-    int qc = Q;
-    while (qc > 1 && box_smem_bytes(qc, D, n_actions, false) > budget) qc = (qc + 1) / 2;
-    if (box_smem_bytes(qc, D, n_actions, false) > budget) return bad_arg(4, "D too large for the tile ring");
+    ScanPlan sp;
+    if (int rc = plan_scan(Q, D, n_actions, buf_is_f64, sp)) return rc;
     PeerCtx pc;
     {
-        const int nmsg = ((Q < qc) ? Q : qc) * n_actions * 3;
-        if (int rc = make_peer_ctx(peers, nmsg, 15, pc)) return rc;
+        const int nmsg = ((Q < sp.qc) ? Q : sp.qc) * n_actions * 3;
+        if (int rc = make_peer_ctx(peers, nmsg, 16, pc)) return rc;
     }
     const int sms = sm_count();
-    const long long n_tiles = (M + kTileRows - 1) / kTileRows;
-    for (int q0 = 0; q0 < Q; q0 += qc) {
-        const int qn = (Q - q0 < qc) ? Q - q0 : qc;
+    for (int q0 = 0; q0 < Q; q0 += sp.qc) {
+        const int qn = (Q - q0 < sp.qc) ? Q - q0 : sp.qc;
         BoxArgs a;
         a.buf_state = buf_state; a.buf_ret = buf_ret; a.M = M; a.D = D; a.Q = qn; a.n_actions = n_actions;
         a.lo = nullptr; a.hi = nullptr; a.dist = dist;
         a.out = acc + (size_t)q0 * n_actions * 3;
-        a.bins_in_smem = (qn * n_actions <= kMaxSmemBins) &&
-                         box_smem_bytes(qn, D, n_actions, true) <= budget;
         a.queries = queries + (size_t)q0 * D;
         a.ticket = ticket;
         a.out_moments = out_moments + (size_t)q0 * n_actions * 3;
@@ -434,21 +743,8 @@ extern "C" int dcarl_box_query(const float *buf_state, const float *buf_ret, int
         a.out_action = out_action ? out_action + q0 : nullptr;
         a.rp = *rp;
         a.peers = pc;
-        const size_t smem = box_smem_bytes(qn, D, n_actions, a.bins_in_smem);
-        int per_sm = (int)((size_t)(220 * 1024) / smem);
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;
-        long long grid = (long long)sms * per_sm;
-        if (grid > n_tiles) grid = n_tiles;
-        if (grid < 1) grid = 1;                                   // an empty shard still takes part in the reduction
-        if (D == 20) {
-            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_box_moments<20, true><<<(unsigned)grid, kTileRows, smem, st>>>(a);
-        } else {
-            DCARL_CUDA(cudaFuncSetAttribute(k_box_moments<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_box_moments<0, true><<<(unsigned)grid, kTileRows, smem, st>>>(a);
-        }
-        DCARL_LAUNCH_CHECK("k_box_moments (fused query)");
+        const int rc = buf_is_f64 ? launch_scan<double, true>(a, sp, sms, st) : launch_scan<float, true>(a, sp, sms, st);
+        if (rc) return rc;
     }
     return 0;
 }

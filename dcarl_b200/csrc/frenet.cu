@@ -31,16 +31,12 @@ constexpr int kFrWarpsPerCta = 4;
 // ---- SPL:18-45, 123-150: natural cubic splines x(s), y(s) through the knots of one route ---------
 // coef rows: {s, ax, bx, cx, dx, ay, by, cy, dy}.  The reference assembles the dense system and
 // calls np.linalg.solve; the system is tridiagonal and strictly diagonally dominant: Thomas.
-__global__ void __launch_bounds__(128) k_spline_build(const double *__restrict__ xy,
-                                                      const long long *__restrict__ knot_off, int n_paths,
-                                                      double *__restrict__ coef) {
-    const int pth = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pth >= n_paths) return;
-    const long long k0 = knot_off[pth];
-    const int n = (int)(knot_off[pth + 1] - k0);
-    if (n < 2) return;
-    const double *q = xy + 2 * k0;
-    double *c = coef + 9 * k0;
+// One warp per route.  The route is staged in shared memory (the serial parts — the running arc length
+// and the two elimination sweeps — then cost a shared-memory round trip per knot instead of a DRAM one):
+// lanes share the row set-up and the final coefficients, lane 0 solves the x system while lane 1 solves
+// the y system.  Every value is computed by the same expression, in the same order, as by the serial
+// form below (routes longer than the staging area fall back to it): results are bitwise the same.
+__device__ void spline_build_serial(const double *q, double *c, int n) {
     double s = 0.0;
     for (int i = 0; i < n; ++i) {
         if (i) {
@@ -78,6 +74,78 @@ __global__ void __launch_bounds__(128) k_spline_build(const double *__restrict__
         }
         B[9 * (n - 1)] = 0.0;
         D[9 * (n - 1)] = 0.0;
+    }
+}
+
+constexpr int kSplineCols = 7;   // staged per knot: s, a_x, a_y, diag_x, rhs_x -> c_x, diag_y, rhs_y -> c_y share slots
+
+__global__ void __launch_bounds__(32) k_spline_build(const double *__restrict__ xy,
+                                                     const long long *__restrict__ knot_off, int n_paths,
+                                                     double *__restrict__ coef, int cap) {
+    extern __shared__ double spl[];
+    const int pth = blockIdx.x, lane = threadIdx.x;
+    if (pth >= n_paths) return;
+    const long long k0 = knot_off[pth];
+    const int n = (int)(knot_off[pth + 1] - k0);
+    if (n < 2) return;
+    const double *q = xy + 2 * k0;
+    double *c = coef + 9 * k0;
+    if (n > cap) {                                  // longer than the staging area: the serial form in place
+        if (lane == 0) spline_build_serial(q, c, n);
+        return;
+    }
+    double *S = spl, *AX = S + cap, *AY = AX + cap, *BX = AY + cap, *DX = BX + cap, *BY = DX + cap, *DY = BY + cap;
+    for (int i = lane; i < n; i += 32) { AX[i] = q[2 * i]; AY[i] = q[2 * i + 1]; }
+    __syncwarp();
+    for (int i = lane + 1; i < n; i += 32) {        // segment lengths (kept in BX until the running sum is taken)
+        const double dx = AX[i] - AX[i - 1], dy = AY[i] - AY[i - 1];
+        BX[i] = sqrt(dx * dx + dy * dy);
+    }
+    __syncwarp();
+    if (lane == 0) {                                // SPL:130-137: a running sum, in knot order
+        double s = 0.0;
+        S[0] = 0.0;
+        for (int i = 1; i < n; ++i) { s += BX[i]; S[i] = s; }
+    }
+    __syncwarp();
+    for (int i = lane + 1; i <= n - 2; i += 32) {   // interior rows of both systems
+        const double h0 = S[i] - S[i - 1], h1 = S[i + 1] - S[i];
+        const double diag = 2.0 * (h0 + h1);
+        BX[i] = diag; BY[i] = diag;
+        DX[i] = 3.0 * (AX[i + 1] - AX[i]) / h1 - 3.0 * (AX[i] - AX[i - 1]) / h0;   // SPL:118-119
+        DY[i] = 3.0 * (AY[i + 1] - AY[i]) / h1 - 3.0 * (AY[i] - AY[i - 1]) / h0;
+    }
+    __syncwarp();
+    if (lane < 2) {                                 // Thomas: lane 0 the x system, lane 1 the y system
+        double *B = lane ? BY : BX, *D = lane ? DY : DX;
+        for (int i = 2; i <= n - 2; ++i) {
+            const double sub = S[i] - S[i - 1];
+            const double l = sub / B[i - 1];
+            B[i] -= l * sub;
+            D[i] -= l * D[i - 1];
+        }
+        double next = 0.0;                          // c of row i+1 (0 at the natural end)
+        for (int i = n - 2; i >= 1; --i) {
+            const double sup = S[i + 1] - S[i];
+            next = (D[i] - (i + 1 <= n - 2 ? sup * next : 0.0)) / B[i];
+            D[i] = next;                            // the rhs slot now holds c
+        }
+        D[0] = 0.0;
+        D[n - 1] = 0.0;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {            // SPL:38-43, and the rows of the output
+        double bx = 0.0, dx = 0.0, by = 0.0, dy = 0.0;
+        if (i < n - 1) {
+            const double h = S[i + 1] - S[i];
+            dx = (DX[i + 1] - DX[i]) / (3.0 * h);
+            bx = (AX[i + 1] - AX[i]) / h - h * (DX[i + 1] + 2.0 * DX[i]) / 3.0;
+            dy = (DY[i + 1] - DY[i]) / (3.0 * h);
+            by = (AY[i + 1] - AY[i]) / h - h * (DY[i + 1] + 2.0 * DY[i]) / 3.0;
+        }
+        double *r = c + 9 * i;
+        r[0] = S[i]; r[1] = AX[i]; r[2] = bx; r[3] = DX[i]; r[4] = dx;
+        r[5] = AY[i]; r[6] = by; r[7] = DY[i]; r[8] = dy;
     }
 }
 
@@ -488,8 +556,11 @@ extern "C" int dcarl_spline_build(const double *knots_xy, const int64_t *knot_of
     if (n_paths == 0) return 0;
     if (!knots_xy || !knot_off) return bad_arg(1, "knots_xy/knot_off is null");
     if (!coef) return bad_arg(4, "coef is null");
-    k_spline_build<<<(unsigned)((n_paths + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        knots_xy, reinterpret_cast<const long long *>(knot_off), n_paths, coef);
+    const int cap = 1792;                                             // knots staged per route: 98 KB of shared memory
+    const size_t smem = (size_t)cap * kSplineCols * sizeof(double);
+    DCARL_CUDA(cudaFuncSetAttribute(k_spline_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_spline_build<<<(unsigned)n_paths, 32, smem, (cudaStream_t)stream>>>(
+        knots_xy, reinterpret_cast<const long long *>(knot_off), n_paths, coef, cap);
     DCARL_LAUNCH_CHECK("k_spline_build");
     return 0;
 }

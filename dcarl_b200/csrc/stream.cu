@@ -57,13 +57,22 @@ __device__ __forceinline__ double u32_to_double(unsigned n) {
 
 // 1/sqrt(x) for positive, normal, finite x: hardware seed (MUFU.RSQ64H, ~2^-20) and one
 // third-order step y(1 + e/2 + 3e^2/8), e = 1 - x y^2; remaining error ~e^3 << 2^-53.
+#ifdef DCARL_V_CONTRACT   // A/B variant: let the compiler contract mul+add pairs (fewer instructions, path-dependent bits)
+#define DMUL(a, b) ((a) * (b))
+#define DADD(a, b) ((a) + (b))
+#define DFMA(a, b, c) fma(a, b, c)
+#else
+#define DMUL(a, b) __dmul_rn(a, b)
+#define DADD(a, b) __dadd_rn(a, b)
+#define DFMA(a, b, c) __fma_rn(a, b, c)
+#endif
 __device__ __forceinline__ double rsqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = __dmul_rn(x, y);
-    const double e = __fma_rn(-t, y, 1.0);
-    const double q = __fma_rn(e, 0.375, 0.5);
-    return __fma_rn(__dmul_rn(y, e), q, y);
+    const double t = DMUL(x, y);
+    const double e = DFMA(-t, y, 1.0);
+    const double q = DFMA(e, 0.375, 0.5);
+    return DFMA(DMUL(y, e), q, y);
 }
 
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
@@ -77,8 +86,8 @@ struct __align__(16) NEntry {
 __device__ __forceinline__ NEntry make_entry(double dn, double c_h) {
     const double rs = rsqrt_pos(dn);
     NEntry e;
-    e.inv_n = __dmul_rn(rs, rs);
-    e.hn = __dmul_rn(c_h, rs);
+    e.inv_n = DMUL(rs, rs);
+    e.hn = DMUL(c_h, rs);
     return e;
 }
 
@@ -93,29 +102,28 @@ __device__ __forceinline__ NEntry make_entry(double dn, double c_h) {
 // constant cell and gives sigma = 0 exactly, like the reference's two-pass np.std on constant samples.
 __device__ __forceinline__ double cell_value_e(const NEntry e0, const NEntry e1, double dn, double s1, double s2,
                                                bool is_rule, double cap) {
-    const double mean = __dmul_rn(s1, e0.inv_n);
+    const double mean = DMUL(s1, e0.inv_n);
     // +hn for the rule action (upper bound), -hn otherwise (lower bound)
     const double hs = __hiloint2double(__double2hiint(e0.hn) ^ (is_rule ? 0 : (int)0x80000000), __double2loint(e0.hn));
-    const double x = __dadd_rn(mean, hs);
-    const double t = __dmul_rn(mean, mean);
-    const double var = __fma_rn(s2, e0.inv_n, -t);
-    // var <= t * n * 2^-50  <=>  var - (t * 2^-50) * n <= 0
+    const double x = DADD(mean, hs);
+    const double t = DMUL(mean, mean);
+    const double var = DFMA(s2, e0.inv_n, -t);
     // var <= t * n * 2^-50  <=>  var - (t * 2^-50) * n <= 0.  The 1/sqrt chain does not wait for the
     // test: it runs on whatever var holds (garbage for var <= 0) and the select discards it.
-    const double sd = __dmul_rn(var, rsqrt_pos(var));
+    const double sd = DMUL(var, rsqrt_pos(var));
 #ifdef DCARL_V_ABS_CLAMP
     const double sigma = var > 1e-280 ? sd : 0.0;
 #else
-    const double sigma = __fma_rn(-__dmul_rn(t, 8.8817841970012523e-16 /* 2^-50 */), dn, var) > 0.0 ? sd : 0.0;
+    const double sigma = DFMA(-DMUL(t, 8.8817841970012523e-16 /* 2^-50 */), dn, var) > 0.0 ? sd : 0.0;
 #endif
-    const double ci = __fma_rn(__dadd_rn(__fma_rn(-4.0, sigma, mean), s1), e1.inv_n, -e1.hn);
+    const double ci = DFMA(DADD(DFMA(-4.0, sigma, mean), s1), e1.inv_n, -e1.hn);
     return dmin(x, is_rule ? cap : ci);
 }
 
 __device__ __forceinline__ double cell_value(unsigned n, double s1, double s2, bool is_rule, double c_h,
                                              double cap) {
     const double dn = u32_to_double(n);
-    return cell_value_e(make_entry(dn, c_h), make_entry(__dadd_rn(dn, 1.0), c_h), dn, s1, s2, is_rule, cap);
+    return cell_value_e(make_entry(dn, c_h), make_entry(DADD(dn, 1.0), c_h), dn, s1, s2, is_rule, cap);
 }
 
 // Runner-up bound kept per state: any value in [second, max) keeps both fast-path tests

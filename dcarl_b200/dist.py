@@ -181,8 +181,12 @@ class ShardedBoxQuery:
     Static output tensors (overwritten by the next call).  Without peer mapping between the ranks the sum
     goes through NCCL between a scan launch and a select launch."""
 
-    def __init__(self, buf, Q, n_actions, rls_params=None, group=None, peers=None):
+    def __init__(self, buf, Q, n_actions, rls_params=None, group=None, peers=None, graph=False):
+        """graph=True replays the launch from a CUDA graph (captured on the first call, re-captured when the
+        buffer grew or moved): the per-query host cost drops to one graph launch.  The peer all-reduce keeps
+        its call counter on the device, so it is captured with the kernel; every rank must use the same setting."""
         self.buf, self.Q, self.na, self.group = buf, int(Q), int(n_actions), group
+        self.use_graph, self._graph, self._key = bool(graph), None, None
         self.rp = rls_params or _abi.RlsParams()
         dev = buf.device
         self.q = torch.zeros((self.Q, buf.D), dtype=torch.float64, device=dev)
@@ -210,9 +214,22 @@ class ShardedBoxQuery:
             allreduce_stats(self.mom, self.group)
             buf.select(self.mom, self.rp, out=(self.mv, self.pick))
             return self.mom, self.mv, self.pick
-        buf.query_fused(q, self.na, self.rp, self.ws, (self.mom, self.mv, self.pick),
-                        self.peers.ctx if self.world > 1 else None)
-        return self.mom, self.mv, self.pick
+        ctx = self.peers.ctx if self.world > 1 else None
+        out = (self.mom, self.mv, self.pick)
+        if not self.use_graph:
+            buf.query_fused(q, self.na, self.rp, self.ws, out, ctx)
+            return out
+        key = (len(buf), buf._state.data_ptr(), buf._ret.data_ptr())
+        self.q.copy_(q, non_blocking=True)
+        if self._graph is None or self._key != key:
+            buf.query_fused(self.q, self.na, self.rp, self.ws, out, ctx)      # warm-up outside the capture
+            torch.cuda.synchronize(buf.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                buf.query_fused(self.q, self.na, self.rp, self.ws, out, ctx)
+            self._graph, self._key = g, key
+        self._graph.replay()
+        return out
 
 
 class MixedStreamBatch:
@@ -272,8 +289,9 @@ def frenet_stats(index, cost):
     hist = torch.bincount(idx.clamp_min(0), minlength=C + 1)[:C + 1].to(torch.float64)
     picked = idx > 0
     sel_cost = cost.gather(1, (idx - 1).clamp_min(0)[:, None])[:, 0].to(torch.float64)
+    # (torch.where, not a product: the selected-cost slot of a scenario without a pick can hold NaN)
     head = torch.stack([torch.tensor(float(idx.numel()), dtype=torch.float64, device=idx.device),
-                        (idx == 0).sum().to(torch.float64), (sel_cost * picked).sum()])
+                        (idx == 0).sum().to(torch.float64), torch.where(picked, sel_cost, torch.zeros_like(sel_cost)).sum()])
     return torch.cat([head, hist])
 
 

@@ -166,7 +166,12 @@ def frenet_start(routes, path_id, ego, *, stream=None):
 class JunctionTrajectoryPlanner(object):
     """Drop-in for JTP:44-290 as the scripts use it (`trajectory_update(dynamic_map)`), one scenario per
     call through the batched kernel.  dynamic_map: .ego_vehicle (x, y, v, vx, vy), .vehicles (x, y, vx,
-    vy, yaw each), .lanes[0].central_path (points with .position.x/.y), .lanes_updated."""
+    vy, yaw each), .lanes[0].central_path (points with .position.x/.y), .lanes_updated.
+
+    Stateful like the reference: the trajectory returned by a tick is kept (update_last_trajectory,
+    JTP:158-161) and a later brake tick (index 0) hands it out again with zeroed speeds whenever it has more
+    than five speed samples and the ego is faster than 1 m/s (get_backup_trajectory, JTP:142-152); only the
+    first tick, a slow ego, or a tick after clear_buff() brake on the cheapest candidate of the tick itself."""
 
     def __init__(self, target_line=0, params=None):
         self.params = params or frenet_params()
@@ -175,8 +180,13 @@ class JunctionTrajectoryPlanner(object):
         self.ref_path = None
         self.all_trajectory = None
         self.last_result = None
+        self.c_speed = 0.0
+        self.last_trajectory_rule = None          # (xy [n, 2], s_d list) of the previous tick's trajectory
 
     def clear_buff(self, clean_csp=True):
+        if self.routes is None:                   # JTP:66-67
+            return
+        self.last_trajectory_rule = None          # JTP:69-72
         if clean_csp:
             self.routes = None
             self.ref_path = None
@@ -192,6 +202,7 @@ class JunctionTrajectoryPlanner(object):
             self.build_frenet_path(dynamic_map, True)
         ego = dynamic_map.ego_vehicle
         start = frenet_start(self.routes, [0], [[ego.x, ego.y, ego.vx, ego.vy, ego.v]])   # JTP:248-276
+        self.c_speed = float(start[0][4])
         veh = list(dynamic_map.vehicles)
         obs = np.array([[v.x, v.y, v.vx, v.vy, v.yaw] for v in veh], np.float64).reshape(1, -1, 5)
         if obs.shape[1] > 32:                                                   # the kernel ranks at most 32
@@ -207,11 +218,28 @@ class JunctionTrajectoryPlanner(object):
     def get_optimal_trajectory(self, path_tuples=None):
         return int(self.last_result.index[0])
 
-    def trajectory_update(self, dynamic_map):
+    def get_trajectory_by_index(self, act_idx, all_trajectory=None):
+        """JTP:132-152 for the tick's selected index: (xy [n, 2], desired speeds); 0 = the backup trajectory."""
+        res = self.last_result
+        if int(act_idx) != int(res.index[0]):
+            raise ValueError("the drop-in class hands out the selected trajectory only; the batched frenet_plan / "
+                             "rollout_candidates cover the other candidates")
+        if int(act_idx) == 0:
+            last = self.last_trajectory_rule
+            if last is not None and len(last[1]) > 5 and self.c_speed > 1:          # JTP:144-146
+                return last[0], [0] * len(last[1])
+        # the kernel's out_traj: the selected candidate, or for index 0 the cheapest one with zeroed speeds (JTP:148-150)
+        n = int(res.traj_len[0])
+        k = int(np.sum(~np.isnan(res.traj[0, :, 2])))
+        return res.traj[0, :n, :2].copy(), res.traj[0, :k, 2].tolist()
+
+    def update_last_trajectory(self, trajectory):                                     # JTP:158-161
+        self.last_trajectory_rule = (np.asarray(trajectory[0], np.float64).copy(), list(trajectory[1]))
+
+    def trajectory_update(self, dynamic_map):                                         # JTP:88-101
         if self.get_all_candidate_trajectories(dynamic_map) is None:
             return None
-        res = self.last_result
-        n = int(res.traj_len[0])
-        nt = int(np.sum(~np.isnan(res.traj[0, :, 2])))
-        action = TrajectoryAction(res.traj[0, :n, :2].copy(), res.traj[0, :nt, 2].tolist())
-        return action, int(res.index[0])
+        index = int(self.last_result.index[0])
+        final = self.get_trajectory_by_index(index)
+        self.update_last_trajectory(final)
+        return TrajectoryAction(final[0], final[1]), index

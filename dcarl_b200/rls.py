@@ -4,8 +4,9 @@ Drop-in for class RLS of Field_testing/.../tools/DCARL/stable_baselines/deepq/RL
 constructor keywords, same methods (act / act_train / act_test / should_use_rule / add_data /
 state_with_action / _calculate_visited_times / _calculate_statistics_index), same files
 (visited_state.txt, visited_value.txt, driving_record.txt in the working directory).  The rtree
-(RLS.py:61-69) is replaced by a float32 device copy of the buffer that one kernel pass scans for
-all candidate actions at once (csrc/box.cu); `state_index.dat/.idx` are neither read nor written.
+(RLS.py:61-69) is replaced by a device copy of the buffer (float64 like the reference's boxes; BoxBuffer
+also offers a float32 throughput layout) that one kernel pass scans for all candidate actions at once
+(csrc/box.cu); `state_index.dat/.idx` are neither read nor written.
 """
 import ctypes as C
 import os
@@ -24,18 +25,27 @@ VISITED_STATE_DIST = np.array([[1, 0.3, 2, 50, 10, 0.3, 2, 50, 10, 0.3, 2, 50, 1
 
 
 class BoxBuffer:
-    """Append-only device buffer {state (+) action float32 [M, D+1], return float32 [M]} + the scan."""
+    """Append-only device buffer {state (+) action [M, D+1], return [M]} + the scan.
 
-    def __init__(self, obs_dimension=20, dist=VISITED_STATE_DIST, capacity=1 << 16, device=None):
+    dtype=torch.float32 (default) is the throughput layout, 4*(D+2) bytes per row; dtype=torch.float64 keeps
+    the reference's own precision (RLS.py:195-196 builds its boxes from float64 rows): a float32 copy moves a
+    stored coordinate by up to 4e-6 at |x| ~ 100, which flips queries that sit that close to a box face
+    (measured: DESIGN.md section 5).  The drop-in RLS class stores float64."""
+
+    def __init__(self, obs_dimension=20, dist=VISITED_STATE_DIST, capacity=1 << 16, device=None, dtype=torch.float32):
         _dev.require_cuda()
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("BoxBuffer dtype must be torch.float32 or torch.float64")
+        self.dtype = dtype
+        self._esize = 8 if dtype == torch.float64 else 4
         self.D = int(obs_dimension)
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         self.dist = _dev.as_device(np.asarray(dist, np.float64).reshape(-1), torch.float64, self.device)
         if self.dist.numel() != self.D + 1:
             raise ValueError("dist must have obs_dimension + 1 entries")
         self.M = 0
-        self._state = torch.empty((capacity, self.D + 1), dtype=torch.float32, device=self.device)
-        self._ret = torch.empty((capacity,), dtype=torch.float32, device=self.device)
+        self._state = torch.empty((capacity, self.D + 1), dtype=dtype, device=self.device)
+        self._ret = torch.empty((capacity,), dtype=dtype, device=self.device)
         self._ws = None
         self._index_dim = None      # see build_index(): rows [0, _index_rows) are sorted by this dim
         self._index_rows = 0
@@ -55,8 +65,8 @@ class BoxBuffer:
 
     def append(self, states, returns):
         """states [m, D+1] (or [D+1]), returns [m]; numpy or tensors."""
-        s = _dev.as_device(states, torch.float32, self.device).reshape(-1, self.D + 1)
-        r = _dev.as_device(returns, torch.float32, self.device).reshape(-1)
+        s = _dev.as_device(states, self.dtype, self.device).reshape(-1, self.D + 1)
+        r = _dev.as_device(returns, self.dtype, self.device).reshape(-1)
         m = s.shape[0]
         if r.numel() != m:
             raise ValueError("one return per stored state expected")
@@ -92,13 +102,19 @@ class BoxBuffer:
         total = int(row_off[-1].item())
         if total == 0:
             return 0
+        if int(off[0].item()) != 0 or int(off[-1].item()) != N or bool((off[1:] < off[:-1]).any()):
+            raise ValueError("ep_offsets must start at 0, end at the number of transitions and be non-decreasing")
         ep_of_row = torch.repeat_interleave(torch.arange(E, dtype=torch.int32, device=self.device), off[1:] - off[:-1])
         self.reserve(self.M + total)
-        st_out = self._state[self.M:self.M + total]
-        rt_out = self._ret[self.M:self.M + total]
+        f32 = self.dtype == torch.float32       # the writer produces float32 rows (its inputs are float32)
+        st_out = self._state[self.M:self.M + total] if f32 else torch.empty((total, self.D + 1), dtype=torch.float32, device=self.device)
+        rt_out = self._ret[self.M:self.M + total] if f32 else torch.empty((total,), dtype=torch.float32, device=self.device)
         _abi.check(L.dcarl_add_data_rows(_dev.ptr(o), _dev.ptr(a), _dev.ptr(r), _dev.ptr(d), _dev.ptr(off),
                                          _dev.ptr(row_off), _dev.ptr(ep_of_row), N, self.D, lag, float(gamma),
                                          _dev.ptr(st_out), _dev.ptr(rt_out), sh))
+        if not f32:
+            self._state[self.M:self.M + total] = st_out
+            self._ret[self.M:self.M + total] = rt_out
         self.M += total
         return total
 
@@ -106,8 +122,8 @@ class BoxBuffer:
         """Grow the device arrays to hold at least `rows` rows (amortised doubling)."""
         if rows > self._state.shape[0]:
             cap = max(2 * self._state.shape[0], rows)
-            ns = torch.empty((cap, self.D + 1), dtype=torch.float32, device=self.device)
-            nr = torch.empty((cap,), dtype=torch.float32, device=self.device)
+            ns = torch.empty((cap, self.D + 1), dtype=self.dtype, device=self.device)
+            nr = torch.empty((cap,), dtype=self.dtype, device=self.device)
             ns[:self.M] = self._state[:self.M]
             nr[:self.M] = self._ret[:self.M]
             self._state, self._ret = ns, nr
@@ -125,10 +141,10 @@ class BoxBuffer:
             ws = self._ws
         elif ws.numel() < need:
             raise ValueError("threshold workspace too small for this query shape")
-        sp = C.c_void_p(self._state.data_ptr() + row_lo * (self.D + 1) * 4)
-        rp = C.c_void_p(self._ret.data_ptr() + row_lo * 4)
+        sp = C.c_void_p(self._state.data_ptr() + row_lo * (self.D + 1) * self._esize)
+        rp = C.c_void_p(self._ret.data_ptr() + row_lo * self._esize)
         with torch.cuda.device(self.device):
-            _abi.check(L.dcarl_box_moments(sp, rp, row_hi - row_lo, self.D, _dev.ptr(self.dist), _dev.ptr(q), Q,
+            _abi.check(L.dcarl_box_moments(sp, rp, int(self._esize == 8), row_hi - row_lo, self.D, _dev.ptr(self.dist), _dev.ptr(q), Q,
                                            n_actions, _dev.ptr(out), _dev.ptr(ws), ws.numel(),
                                            _dev.stream_handle(stream)))
         self.last_scanned_rows += (row_hi - row_lo) if Q else 0
@@ -142,7 +158,7 @@ class BoxBuffer:
         L = _abi.lib()
         with torch.cuda.device(self.device):
             _abi.check(L.dcarl_box_query(
-                _dev.ptr(self._state), _dev.ptr(self._ret), self.M, self.D, _dev.ptr(self.dist), _dev.ptr(q),
+                _dev.ptr(self._state), _dev.ptr(self._ret), int(self._esize == 8), self.M, self.D, _dev.ptr(self.dist), _dev.ptr(q),
                 q.shape[0], n_actions, rls_params or _abi.RlsParams(), _dev.ptr(mom), _dev.ptr(mv), _dev.ptr(pick),
                 C.c_void_p((ws.data_ptr() + 15) & ~15), ws.numel() - 16, C.byref(peer_ctx) if peer_ctx is not None else None,
                 _dev.stream_handle(stream)))
@@ -195,11 +211,11 @@ class BoxBuffer:
             out = torch.empty((Q, n_actions, 3), dtype=torch.float64, device=self.device)
         d = self._index_dim
         w = self.dist[d]
-        # float32 bracket, widened by 2 ulp: a prefilter only, the kernel applies the exact test
-        lo = torch.nextafter(torch.nextafter((q[:, d] - w).float(), torch.tensor(-float("inf"), device=self.device)),
-                             torch.tensor(-float("inf"), device=self.device))
-        hi = torch.nextafter(torch.nextafter((q[:, d] + w).float(), torch.tensor(float("inf"), device=self.device)),
-                             torch.tensor(float("inf"), device=self.device))
+        # bracket in the buffer's element type, widened by 2 ulp: a prefilter only, the kernel applies the exact test
+        ninf = torch.tensor(-float("inf"), device=self.device, dtype=self.dtype)
+        pinf = torch.tensor(float("inf"), device=self.device, dtype=self.dtype)
+        lo = torch.nextafter(torch.nextafter((q[:, d] - w).to(self.dtype), ninf), ninf)
+        hi = torch.nextafter(torch.nextafter((q[:, d] + w).to(self.dtype), pinf), pinf)
         r0 = torch.searchsorted(self._index_col, lo, right=False).cpu().tolist()
         r1 = torch.searchsorted(self._index_col, hi, right=True).cpu().tolist()
         self.last_scanned_rows = 0
@@ -308,7 +324,8 @@ class RLS(object):
     # RLS.py:34-76
     def _setup_data_saving(self):
         self.visited_state_dist = VISITED_STATE_DIST.copy()
-        self.visited_state_tree = BoxBuffer(self.obs_dimension, self.visited_state_dist)
+        # float64 storage: the reference's boxes are built from float64 rows (RLS.py:195-196)
+        self.visited_state_tree = BoxBuffer(self.obs_dimension, self.visited_state_dist, dtype=torch.float64)
         if self.create_new_train_file:
             for f in ("visited_state.txt", "visited_value.txt"):
                 if osp.exists(f):

@@ -158,7 +158,7 @@ class StreamPlan:
                      C.c_void_p(self.activation_step.data_ptr() + lo * self.S * 8), off(self.overall, ob),
                      C.c_void_p(self.ws.data_ptr() + (lo * (self._ws_bytes // max(self.n_inst, 1)))), stream)
 
-    def run_pinned(self, chunks=4):
+    def run_pinned(self, chunks=8):
         """Inputs already in the plan's pinned host buffers (``plan.pinned()['idx'|'act'|'R']``).
         Instances are cut into `chunks` pieces that flow through three streams — host->device copy,
         kernel, device->host copy — so the two PCIe directions and the kernel overlap.  Returns the

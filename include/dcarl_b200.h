@@ -192,15 +192,18 @@ int dcarl_sample_returns_philox(const void *q_star, int q_is_f64, uint64_t seed,
                                 int out_is_f64, dcarl_stream_t stream);
 
 /* ---- a9-a11: box-kernel confidence, RLS:161-181 and RLS.act_test, RLS:120-157 ------------
- * Buffer: M stored rows, buf_state float32 [M, D+1] (D observation dims, then the action),
- * buf_ret float32 [M] (the return, column 1 of visited_value, RLS:174).  Row i covers the
- * closed box [s_i - dist, s_i + dist] evaluated in float64 (RLS:195-196); a query point
- * obs (+) a (RLS:91-93) matches the rows whose box contains it.  For each of the Q queries
- * (float64 [Q, D]) and each candidate action a in [0, n_actions) writes the raw moments
- * out_moments[q, a, {0,1,2}] = {n, sum R, sum R^2} (float64; zeroed by the call).
- * The kernel is one streaming pass over the buffer: 4*(D+2) bytes per row, independent of Q. */
+ * Buffer: M stored rows, buf_state [M, D+1] (D observation dims, then the action) and buf_ret [M] (the
+ * return, column 1 of visited_value, RLS:174), both float32 (buf_is_f64 == 0: the throughput layout,
+ * 4*(D+2) = 88 bytes per row) or both float64 (buf_is_f64 != 0: the reference's own precision,
+ * RLS:195-196 — a float32 copy moves a stored coordinate by up to 4e-6 at |x| ~ 100, enough to flip a
+ * query that sits that close to a box face).  Row i covers the closed box [s_i - dist, s_i + dist]
+ * evaluated in float64; a query point obs (+) a (RLS:91-93) matches the rows whose box contains it.
+ * For each of the Q queries (float64 [Q, D]) and each candidate action a in [0, n_actions) writes the
+ * raw moments out_moments[q, a, {0,1,2}] = {n, sum R, sum R^2} (float64; zeroed by the call).
+ * One streaming pass over the buffer, independent of Q (many queries on a float32 buffer go through a
+ * bit-signature pre-filter so that the pass stays close to HBM-bound). */
 size_t dcarl_box_moments_ws(int32_t Q, int32_t D, int32_t n_actions);
-int dcarl_box_moments(const float *buf_state, const float *buf_ret, int64_t M, int32_t D,
+int dcarl_box_moments(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
                       const double *dist /* [D+1] */, const double *queries /* [Q, D] */,
                       int32_t Q, int32_t n_actions, double *out_moments,
                       void *ws, size_t ws_bytes, dcarl_stream_t stream);
@@ -211,7 +214,7 @@ int dcarl_box_moments(const float *buf_state, const float *buf_ret, int64_t M, i
  * leaves it zeroed again (no memset per query).  out_moments [Q, n_actions, 3] holds the totals over all
  * ranks; out_mean_var / out_action as in dcarl_box_select (each nullable). */
 size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions);
-int dcarl_box_query(const float *buf_state, const float *buf_ret, int64_t M, int32_t D,
+int dcarl_box_query(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
                     const double *dist /* [D+1] */, const double *queries /* [Q, D] */,
                     int32_t Q, int32_t n_actions, const dcarl_rls_params *p /* host */,
                     double *out_moments, double *out_mean_var, int32_t *out_action,

@@ -115,6 +115,25 @@ class BoxBuffer:
         var = np.var(value_array)
         return mean, var, np.sqrt(var)
 
+    # RLS:95-118 (the debug prints removed); draws from the global `random` like the reference
+    def should_use_rule(self, obs, visited_times_thres=30):
+        import random
+        rule_state = np.append(obs, 0)
+        visited_times_rule = self.calculate_visited_times(rule_state)
+        mean_rule, var_rule, sigma_rule = self.calculate_statistics_index(rule_state)
+        if visited_times_rule < visited_times_thres:
+            return True
+        explore_motivation = random.uniform(-1, 0)
+        if explore_motivation < mean_rule:
+            return True
+        return False
+
+    # RLS:84-89
+    def act_train(self, obs, RL_action, visited_times_thres=30):
+        if self.should_use_rule(obs, visited_times_thres):
+            return np.array(0)
+        return RL_action
+
     # RLS:120-157
     def act_test(self, obs, visited_times_thres=10, confidence_thres=0.5, n_actions=8):
         from scipy.stats import norm

@@ -71,3 +71,17 @@ def recompute_from_traces(idx, value, act, S, rule_act=0, bonus=0.9):
             activation[s] = count[s]
         overall[k] = (last[activated] + bonus).sum()
     return activation, overall
+
+
+def face_queries(states, dist, n, seed, eps=1e-5):
+    """n query observations that sit within +-eps of a face of some stored row's box: the row's own
+    observation, with one coordinate moved to (stored value +- half-width) + U(-eps, eps).  Returns
+    (queries [n, D], action of the row [n])."""
+    rng = np.random.default_rng(seed)
+    D = states.shape[1] - 1
+    rows = rng.integers(0, len(states), n)
+    dim = rng.integers(0, D, n)
+    sign = rng.choice([-1.0, 1.0], n)
+    q = states[rows, :D].astype(np.float64).copy()
+    q[np.arange(n), dim] += sign * dist[dim] + rng.uniform(-eps, eps, n)
+    return q, states[rows, D].astype(np.int64)

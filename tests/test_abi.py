@@ -56,8 +56,19 @@ def test_argument_validation_needs_no_device():
     rc = L.dcarl_stream_bounds(None, None, None, 0, 1, 1, 20, 11, _abi.Params(rule_act=11), None, 0, None, None, None,
                                None, None, None, 0, 0, None)
     assert rc == -9 and b"rule_act" in L.dcarl_last_error()
-    rc = L.dcarl_box_moments(None, None, -1, 20, None, None, 1, 8, None, None, 0, None)
-    assert rc == -3
+    rc = L.dcarl_box_moments(None, None, 0, -1, 20, None, None, 1, 8, None, None, 0, None)
+    assert rc == -4
+    rc = L.dcarl_box_query(None, None, 1, 5, 0, None, None, 1, 8, _abi.RlsParams(), None, None, None, None, 0, None, None)
+    assert rc == -5 and b"D must be" in L.dcarl_last_error()
+    bad = _abi.PeerCtx()
+    bad.world, bad.rank, bad.n_max = 99, 0, 8
+    assert L.dcarl_peer_allreduce(C.c_void_p(16), 4, C.byref(bad), None) == -3 and b"DCARL_MAX_PEERS" in L.dcarl_last_error()
+    assert L.dcarl_peer_ws_bytes(8, 768) >= 2 * 8 * 768 * 8 + 2 * 8 * 4 + 4
+    rp = _abi.RolloutParams()
+    L.dcarl_default_rollout_params(C.byref(rp))
+    assert (rp.dt, rp.robot_radius, rp.ticks_per_point, rp.collision_reward, rp.pass_y, rp.n_pred) == (0.3, 1.0, 6.0, -100.0, 73.7, 15)
+    assert L.dcarl_rollout_candidates(None, None, None, None, None, None, 0, 5, 40, 14, rp, None, None, None, None) == -9
+    assert L.dcarl_stream_bounds_u8(None, None, None, 1, 1, 300, 4, p, None, None, None, None, None, None, None) == -13
     rc = L.dcarl_bounds(None, 1, None, 3, _abi.Params(alpha=0.0), None, None)
     assert rc == -5 and b"alpha" in L.dcarl_last_error()
     with pytest.raises(_abi.DcarlError):

@@ -173,8 +173,8 @@ def test_rls_class_drop_in(tmp_path, golden, monkeypatch):
         rls.add_data(far + t, 1, 0.0 if t < 14 else -1.0, far + t + 1, t == 14)
     assert len(rls.visited_state_tree) == before + 15
     tail = rls.visited_state_tree.ret[before:].cpu().numpy()
-    want = np.array([r for _, r in pyref.add_data_returns([0.0] * 14 + [-1.0], [False] * 14 + [True])], np.float32)
-    assert np.array_equal(tail, want)
+    want = np.array([r for _, r in pyref.add_data_returns([0.0] * 14 + [-1.0], [False] * 14 + [True])], np.float64)
+    assert tail.dtype == np.float64 and np.array_equal(tail, want)          # the drop-in stores float64 like the reference
     rls.visited_state_outfile.flush(); rls.driving_record_outfile.flush()
     assert len(open("visited_state.txt").readlines()) == len(vs) + 15
     rec = np.loadtxt("driving_record.txt")
@@ -182,6 +182,47 @@ def test_rls_class_drop_in(tmp_path, golden, monkeypatch):
     # should_use_rule: under-visited rule action -> rule
     rls.is_training = True
     assert int(rls.act(far, np.array(5))) == 0
+
+
+def test_training_mode_gate_follows_the_reference_draw_for_draw(tmp_path, golden, monkeypatch):
+    """should_use_rule / act_train (RLS.py:84-118) with a seeded `random`: the under-visited branch, and the
+    exploration branch `random.uniform(-1, 0) < mean_rule` on both of its outcomes, against the literal port
+    consuming the same random stream."""
+    import random
+    g = golden("rls_box")
+    vs, vv, dr = g["visited_state"], g["visited_value"], g["driving_record"]
+    monkeypatch.chdir(tmp_path)
+    np.savetxt("visited_state.txt", vs, fmt="%f")
+    np.savetxt("visited_value.txt", vv, fmt="%f")
+    rls = dc.RLS(visited_times_thres=10, is_training=True, debug=False, save_new_data=False,
+                 create_new_train_file=False, create_new_record_file=True, save_new_driving_data=False)
+    lit = pyref.BoxBuffer(np.loadtxt("visited_state.txt"), np.loadtxt("visited_value.txt"))
+    # stored observations whose rule action is well visited and whose mean return lies inside (-1, 0)
+    rows = np.nonzero((vs[:, 20] == 0) & (vv[:, 1] < -0.3))[0]               # neighbourhoods with negative returns
+    raw = cport.box_raw(vs, vv[:, 1], g["dist"].ravel(), vs[rows, :20], 1, threads=4)
+    mean = raw[:, 0, 1] / np.maximum(raw[:, 0, 0], 1)
+    cand = [int(r) for r, n, m in zip(rows, raw[:, 0, 0], mean) if n >= 10 and -0.9 < m < -0.1]
+    assert len(cand) >= 5
+    dr = vs                                   # (the loop below indexes observations by row)
+    outcomes = set()
+    for seed in range(6):
+        for i in cand[:12]:
+            obs = dr[i, :20]
+            random.seed(1000 * seed + i)
+            want = bool(lit.should_use_rule(obs, visited_times_thres=10))
+            state_after = random.getstate()
+            random.seed(1000 * seed + i)
+            got = rls.should_use_rule(obs)
+            assert got == want and random.getstate() == state_after          # same decision, same number of draws
+            random.seed(1000 * seed + i)
+            a = rls.act(obs, np.array(4))                                     # is_training -> act_train
+            assert int(a) == (0 if want else 4)
+            outcomes.add(want)
+    assert outcomes == {True, False}
+    far = np.full(20, 1e4)                                                    # under-visited: rule, and no draw at all
+    random.seed(5)
+    s0 = random.getstate()
+    assert rls.should_use_rule(far) is True and random.getstate() == s0
 
 
 def test_query_graph_replay_matches_the_plain_path_and_tracks_appends():
@@ -271,6 +312,84 @@ def test_stats_chain_of_a_mixed_batch():
         got2 = mb.run([d1, d2])
         torch.cuda.synchronize()
         assert got.numel() == 35 and torch.equal(got, want) and torch.equal(got2, want)
+
+
+def test_float64_storage_is_exact_on_box_faces_and_float32_is_its_own_oracle(golden):
+    """Queries within +-1e-5 of box faces of the shipped buffer: the float64 device buffer reproduces the
+    float64 oracle count for count (the reference's precision, RLS.py:195-196); the float32 buffer reproduces
+    the oracle on the narrowed rows, and differs from the float64 one on a fraction of a percent of them."""
+    from helpers import face_queries
+    g = golden("rls_box")
+    vs, vv, dist = g["visited_state"], g["visited_value"], g["dist"].ravel()
+    q, _ = face_queries(vs, dist, 6000, seed=9)
+    want64 = cport.box_raw(vs, vv[:, 1], dist, q, 8, threads=4)
+    want32 = cport.box_raw(vs.astype(np.float32), vv[:, 1].astype(np.float32), dist, q, 8, threads=4)
+    b64 = dc.BoxBuffer(20, dtype=torch.float64)
+    b64.append(vs, vv[:, 1])
+    b32 = dc.BoxBuffer(20)
+    b32.append(vs, vv[:, 1])
+    from dcarl_b200 import dist as dd
+    for buf, want in ((b64, want64), (b32, want32)):
+        mom = buf.moments(q, 8).cpu().numpy()
+        assert np.array_equal(mom[:, :, 0], want[:, :, 0])
+        assert np.abs(mom[:, :, 1:] - want[:, :, 1:]).max() < 1e-9
+        fq = dd.ShardedBoxQuery(buf, 64, 8)                                  # the fused launch, same answer
+        fm, _, _ = fq(q[:64])
+        assert np.array_equal(fm[:, :, 0].cpu().numpy(), want[:64, :, 0])
+    assert (want64[:, :, 0] != want32[:, :, 0]).any()
+    # the drop-in class stores float64
+    n64, mean64, var64, pick64 = b64.query(g["driving_record"][:, :20], 8)
+    assert np.array_equal(n64[:, 0], g["driving_record"][:, 23])
+    # the sorted index and appended tails work in float64 too
+    b64.build_index()
+    assert np.array_equal(b64.moments_indexed(q[:5], 8).cpu().numpy()[:, :, 0], want64[:5, :, 0])
+
+
+def test_many_queries_take_the_signature_filter_and_agree_with_the_plain_scan():
+    """Q >= 8 on a float32 buffer of 20 dims: per-dimension bitmap pre-filter + exact test on the survivors.  Counts
+    must equal the oracle's for clustered data, for queries far outside the data, for duplicate queries, NaN
+    queries and rows on the edge of the queries' range."""
+    rng = np.random.default_rng(77)
+    centers, vs, ret = _clustered(rng, n_centers=70, n_actions=9, max_rows=25)
+    vs = np.vstack([vs, np.hstack([centers[:30] + DIST[:20], np.zeros((30, 1))])])     # rows exactly on a box face
+    ret = np.concatenate([ret, -np.ones(30)])
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, ret)
+    q = np.vstack([centers[:60], centers[:2], centers[5:7] + 1e3, centers[:1] * np.nan, centers[3:4] - 0.999 * DIST[:20]])
+    assert len(q) == 66                                                                 # > 64: two filtered launches
+    for Q in (8, 33, 64, 66):
+        mom = buf.moments(q[:Q], 9).cpu().numpy()
+        want = _oracle_nmv(vs, ret, q[:Q], 9)
+        raw = cport.box_raw(_f32(vs).astype(np.float32), _f32(ret).astype(np.float32), DIST, np.nan_to_num(q[:Q], nan=1e30), 9)
+        assert np.array_equal(mom[:, :, 0], want[:, :, 0]), Q
+        assert np.array_equal(mom[:, :, 0], raw[:, :, 0]) and np.abs(mom[:, :, 1:] - raw[:, :, 1:]).max() < 1e-9
+    assert mom[:60, :, 0].sum() > 500 and mom[62:65].sum() == 0
+
+
+def test_many_queries_on_a_buffer_of_many_tiles_per_cta():
+    """The tile ring of the filtered scan wraps several times per CTA (700 001 rows = 2 735 tiles over at most
+    296 CTAs, ragged last tile), with the bins in global memory (64 x 40 > 1024) and in shared memory (64 x 8):
+    counts equal the C oracle's on the same float32 rows; the fused launch gives the same totals."""
+    rng = np.random.default_rng(5)
+    M, na = 700_001, 40
+    centers = rng.normal(0, 1.5, (3000, 20)) * DIST[:20]
+    which = rng.integers(0, len(centers), M)
+    vs = np.hstack([centers[which] + rng.uniform(-0.6, 0.6, (M, 20)) * DIST[:20],
+                    rng.integers(0, na, (M, 1)).astype(np.float64)]).astype(np.float32)
+    ret = (-0.95 ** rng.integers(0, 10, M) * (rng.random(M) < 0.5)).astype(np.float32)
+    buf = dc.BoxBuffer(20, capacity=M)
+    buf.append(vs, ret)
+    q = centers[rng.integers(0, len(centers), 64)] + rng.uniform(-0.3, 0.3, (64, 20)) * DIST[:20]
+    from dcarl_b200 import dist as dd
+    for n_actions in (na, 8):
+        raw = cport.box_raw(vs, ret, DIST, q, n_actions, threads=8)
+        mom = buf.moments(q, n_actions).cpu().numpy()
+        assert np.array_equal(mom[:, :, 0], raw[:, :, 0]) and raw[:, :, 0].sum() > 2000
+        assert np.abs(mom[:, :, 1:] - raw[:, :, 1:]).max() < 1e-9
+        fm, _, _ = dd.ShardedBoxQuery(buf, 64, n_actions)(q)
+        assert np.array_equal(fm[:, :, 0].cpu().numpy(), raw[:, :, 0])
+        one = buf.moments(q[:1], n_actions).cpu().numpy()                  # the plain scan agrees
+        assert np.array_equal(one[0, :, 0], raw[0, :, 0])
 
 
 def test_batched_add_data_matches_the_reference_deque():

@@ -268,3 +268,28 @@ def test_collect_and_select_closes_the_loop_on_the_device():
                     np.where(ref[:, :, 0] > 0, np.maximum(ref[:, :, 2] / nn - (ref[:, :, 1] / nn) ** 2, 0), -1.0)], 2)
     assert np.array_equal(out["action"].cpu().numpy(), cport.box_select(nmv, visited_times_thres=10))
     assert np.abs(out["mean"].cpu().numpy() - nmv[:, :, 1]).max() < 1e-9
+
+
+def test_drop_in_planner_hands_over_the_previous_trajectory_on_brake_ticks(golden):
+    """Consecutive ticks against the reference driven the same way (tools/make_golden_frenet_ticks.py): a brake
+    tick returns the PREVIOUS tick's trajectory with zeroed speeds (JTP:142-152) unless the ego is slower than
+    1 m/s or there is no previous trajectory."""
+    t = golden("frenet_ticks")
+    NS = types.SimpleNamespace
+    brake_ticks = 0
+    for e in range(int(t["n_episodes"])):
+        lane = [NS(position=NS(x=float(x), y=float(y))) for x, y in t[f"e{e}_lane"]]
+        planner = dc.JunctionTrajectoryPlanner()
+        for k in range(int(t[f"e{e}_n"])):
+            eg = t[f"e{e}_t{k}_ego"]
+            ego = NS(x=float(eg[0]), y=float(eg[1]), vx=float(eg[2]), vy=float(eg[3]), v=float(eg[4]), yaw=float(eg[5]))
+            veh = [NS(x=o[0], y=o[1], vx=o[2], vy=o[3], yaw=o[4]) for o in t[f"e{e}_t{k}_obs"]]
+            dm = NS(ego_vehicle=ego, vehicles=veh, lanes=[NS(central_path=lane)], lanes_updated=False)
+            action, index = planner.trajectory_update(dm)
+            want_xy, want_v = t[f"e{e}_t{k}_traj"], t[f"e{e}_t{k}_speed"]
+            assert index == int(t[f"e{e}_t{k}_index"]), (e, k)
+            assert action.trajectory.shape == want_xy.shape, (e, k)
+            assert np.abs(action.trajectory - want_xy).max() < 1e-8, (e, k)
+            assert len(action.desired_speed) == len(want_v) and np.abs(np.array(action.desired_speed) - want_v).max() < 1e-8
+            brake_ticks += index == 0
+    assert brake_ticks >= 5

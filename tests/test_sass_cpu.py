@@ -59,6 +59,10 @@ def test_register_budget_of_the_row_kernel():
 
 
 def test_box_scan_uses_bulk_copies():
-    sass = [s for _, s in _sass("k_box_momentsILi20E")]
-    assert any("UBLKCP" in s for s in sass)                      # 1-D TMA tile loads
-    assert any("SYNCS" in s for s in sass)                       # mbarrier arrive / wait
+    for sym in ("k_box_momentsIfLi20ELb1E", "k_box_momentsIdLi20ELb1E", "k_box_filterILb1E"):
+        sass = [s for _, s in _sass(sym)]                        # float32 fused, float64 fused, float32 fused + filter
+        assert any("UBLKCP" in s for s in sass)                  # 1-D TMA tile loads
+        assert any("SYNCS" in s for s in sass)                   # mbarrier arrive / wait
+    filt = [s for _, s in _sass("k_box_filterILb0E")]
+    assert sum("LDS.64" in s for s in filt) >= 40                # one bin-geometry and one bitmap-table entry per observation dim
+    assert any("VOTE" in s for s in filt)                        # the warp-wide early exit

@@ -21,15 +21,14 @@ jtp = mg.jtp
 NS = types.SimpleNamespace
 
 
-def wall(ego, n=6):
-    """Slow vehicles spread across the corridor 6-12 m ahead of the ego: every candidate collides."""
+def wall(ego):
+    """Stopped vehicles on the lane where every candidate still is at the first sampled steps t = 2, 4, 6 of
+    predict.check_collision (the candidates only fan out later; 4 vehicles are considered, JTP:28)."""
     u = np.array([np.cos(ego.yaw), np.sin(ego.yaw)])
-    nrm = np.array([-u[1], u[0]])
     out = []
-    for j in range(n):
-        for ahead in (5.0, 8.0, 11.0):
-            q = np.array([ego.x, ego.y]) + u * ahead + nrm * (-5.0 + 10.0 * j / (n - 1))
-            out.append(NS(x=float(q[0]), y=float(q[1]), vx=0.0, vy=0.0, yaw=float(ego.yaw)))
+    for t in (2, 4, 6):
+        q = np.array([ego.x, ego.y]) + u * max(ego.v, 1.0) * 0.3 * t
+        out.append(NS(x=float(q[0]), y=float(q[1]), vx=0.0, vy=0.0, yaw=float(ego.yaw)))
     return out
 
 
