@@ -81,11 +81,17 @@ struct BoxArgs {
     int D, Q, n_actions;
     const void *lo, *hi;       // [Q, D] thresholds in the buffer's element type (unfused path)
     const double *dist;  // [D+1]; dist[D] is the action tolerance
-    double *out;  // [Q, n_actions, 3]; the accumulator (zero on entry) in the fused query
+    double *out;  // [Q, n_actions, 3], zero on entry: the totals of the unfused scan
     int bins_in_smem;
-    // fused query (k_box_moments<.., true>): thresholds in the prologue, reduction + select in the epilogue
+    // fused query (FUSED kernels): thresholds in the prologue, reduction + select in the epilogue.  Two
+    // accumulators alternate between calls (hdr[1] counts the calls): a call adds into one and zeroes the other
+    // for the next call on its way in, spread over all CTAs, so nothing is memset or copied per query.
     const double *queries;     // [Q, D]
-    unsigned *ticket;          // CTAs that have flushed their bins; the last one runs the epilogue and resets it
+    unsigned *hdr;             // {ticket: CTAs that have flushed their bins, calls, extent: doubles the last call used}
+    double *acc[2];            // the two accumulators (whole workspace halves)
+    unsigned q0_off;           // this launch's first accumulator element (queries are chunked over launches)
+    unsigned n3_total;         // accumulator elements of the whole call
+    int last_launch;           // the last launch of a call advances hdr[1]
     double *out_moments;       // [Q, n_actions, 3] totals (summed over ranks when peers.world > 1)
     double *out_mv;            // [Q, n_actions, 2], nullable
     int *out_action;           // [Q], nullable
@@ -143,84 +149,83 @@ __device__ __forceinline__ void box_select_one(const double *m, int n_actions, c
     if (out_action) *out_action = pick;
 }
 
-// Fused epilogue of a scan launch (all threads of every CTA call it after their bins reached p.out): the last
-// CTA to arrive owns the totals — it moves them to out_moments (leaving the accumulator and the ticket zeroed
-// for the next call), adds the other ranks' totals through peer memory, and evaluates (mean, var) and the
-// act_test pick.
-__device__ __forceinline__ void box_epilogue(const BoxArgs &p, const int tid, const int nthr) {
+// Fused prologue (every thread of every CTA): this call's accumulator, and the other one zeroed for the next call.
+__device__ __forceinline__ double *box_fused_accumulator(const BoxArgs &p, const int tid, const int nthr) {
+    const unsigned calls = p.hdr[1], ext = p.hdr[2];
+    double *oth = p.acc[(calls & 1u) ^ 1u];
+    const unsigned nz = ext > p.n3_total ? ext : p.n3_total;
+    for (unsigned i = blockIdx.x * (unsigned)nthr + tid; i < nz; i += gridDim.x * (unsigned)nthr) oth[i] = 0.0;
+    return p.acc[calls & 1u] + p.q0_off;
+}
+
+// Fused epilogue of a scan launch (all threads of every CTA call it after their bins reached the accumulator
+// `acc`): the last CTA to arrive owns the totals — it adds the other ranks' totals through peer memory and
+// writes out_moments, (mean, var) and the act_test pick in one pass over the (query, action) pairs.
+__device__ __forceinline__ void box_epilogue(const BoxArgs &p, const double *acc, double *scratch /* shared, 3 Q doubles */,
+                                             const int tid, const int nthr) {
     const int nbins = p.Q * p.n_actions;
-    // ---- fused epilogue: the last CTA to arrive owns the totals
     __shared__ unsigned s_ticket;
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+    if (tid == 0) s_ticket = atomicAdd(p.hdr, 1u);
     __syncthreads();
     if (s_ticket != gridDim.x - 1u) return;
     __threadfence();
-    // totals of this GPU -> out_moments; the accumulator and the ticket are left zeroed for the next call
-    // (one CTA moves up to 400 KB here: eight independent loads in flight per thread, L2 latency each)
-    {
-        double *__restrict__ acc = p.out;
-        double *__restrict__ tot = p.out_moments;
-        const int n3 = nbins * 3;
-        for (int i0 = 0; i0 < n3; i0 += nthr * 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int i = i0 + u * nthr + tid; v[u] = i < n3 ? __ldcg(acc + i) : 0.0; }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * nthr + tid;
-                if (i < n3) { acc[i] = 0.0; tot[i] = v[u]; }
-            }
-        }
+    const bool solo = p.peers.world <= 1;
+    const double *mom = acc;                 // totals: the accumulator itself, or out_moments after the sum over ranks
+    if (!solo) {
+        peer_allreduce_cta(acc, p.out_moments, nbins * 3, p.peers);
+        __syncthreads();
+        mom = p.out_moments;
     }
-    if (tid == 0) *p.ticket = 0u;
+    // one (query, action) pair per thread and round, the loads of four pairs in flight (this is one CTA: L2
+    // latency, not bandwidth).  The pick is the smallest action index that passes the gate and the z-test
+    // (RLS.py:135-154): an atomic min.
+    // (the rule action's statistics once per query, not once per pair: double divisions are what this CTA spends
+    // its time on)
+    for (int q = tid; q < p.Q; q += nthr) {
+        if (p.out_action) p.out_action[q] = 0x7fffffff;
+        const double *m0 = mom + (size_t)q * p.n_actions * 3;
+        const double n0 = __ldcg(m0);
+        const double mean0 = n0 > 0.0 ? __ldcg(m0 + 1) / n0 : -1.0;
+        scratch[3 * q] = n0;
+        scratch[3 * q + 1] = mean0;
+        scratch[3 * q + 2] = n0 > 0.0 ? fmax(__ldcg(m0 + 2) / n0 - mean0 * mean0, 0.0) : -1.0;
+    }
     __syncthreads();
-    if (p.peers.world > 1) peer_allreduce_cta(p.out_moments, p.out_moments, nbins * 3, p.peers);
-    __syncthreads();
-    // (mean, var) of every (query, action) pair and the act_test pick, one pair per thread and round (no
-    // barrier per query: with 64 queries a per-query loop in this one CTA took longer than the scan).  The pick
-    // is the smallest action index that passes the gate and the z-test (RLS.py:135-154): an atomic min.
-    if (p.out_action)
-        for (int q = tid; q < p.Q; q += nthr) p.out_action[q] = 0x7fffffff;
-    __syncthreads();
-    {
-        const double *mom = p.out_moments;   // (written above by this CTA: plain loads, no read-only path)
-        double *mv = p.out_mv;
-        for (int i0 = 0; i0 < nbins; i0 += nthr * 4) {
-            double n_[4], s1_[4], s2_[4], n0_[4], r1_[4], r2_[4];
+    for (int i0 = 0; i0 < nbins; i0 += nthr * 4) {
+        double n_[4], s1_[4], s2_[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {                       // all loads of four pairs first
-                const int i = min(i0 + u * nthr + tid, nbins - 1);
-                const int q = i / p.n_actions;
-                n_[u] = mom[(size_t)i * 3]; s1_[u] = mom[(size_t)i * 3 + 1]; s2_[u] = mom[(size_t)i * 3 + 2];
-                const double *m0 = mom + (size_t)q * p.n_actions * 3;
-                n0_[u] = m0[0]; r1_[u] = m0[1]; r2_[u] = m0[2];
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int i = min(i0 + u * nthr + tid, nbins - 1);
+            n_[u] = __ldcg(mom + (size_t)i * 3); s1_[u] = __ldcg(mom + (size_t)i * 3 + 1); s2_[u] = __ldcg(mom + (size_t)i * 3 + 2);
+        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * nthr + tid;
-                if (i >= nbins) continue;
-                const int q = i / p.n_actions, a = i - q * p.n_actions;
-                const double n0 = n0_[u];
-                const double mean0 = n0 > 0.0 ? r1_[u] / n0 : -1.0;
-                const double var0 = n0 > 0.0 ? fmax(r2_[u] / n0 - mean0 * mean0, 0.0) : -1.0;
-                const double n = n_[u];
-                double mean = -1.0, var = -1.0;                                    // RLS.py:169-170
-                if (n > 0.0) { mean = s1_[u] / n; var = fmax(s2_[u] / n - mean * mean, 0.0); }
-                if (mv) { mv[(size_t)i * 2] = mean; mv[(size_t)i * 2 + 1] = var; }
-                if (!p.out_action || a == 0 || n0 < (double)p.rp.visited_times_thres ||
-                    n < (double)p.rp.min_candidate_visits || mean0 > p.rp.rule_mean_gate)
-                    continue;                                                      // RLS.py:141
-                const double z = (mean - mean0) / sqrt(var0 / n0 + var / n);     // RLS.py:144-148
-                if (0.5 * erfc(-z * 0.70710678118654752440) > p.rp.confidence_thres) atomicMin(p.out_action + q, a);   // RLS.py:150-154
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * nthr + tid;
+            if (i >= nbins) continue;
+            const int q = i / p.n_actions, a = i - q * p.n_actions;
+            if (solo) { p.out_moments[(size_t)i * 3] = n_[u]; p.out_moments[(size_t)i * 3 + 1] = s1_[u]; p.out_moments[(size_t)i * 3 + 2] = s2_[u]; }
+            const double n0 = scratch[3 * q], mean0 = scratch[3 * q + 1], var0 = scratch[3 * q + 2];
+            const double n = n_[u];
+            double mean = -1.0, var = -1.0;                                    // RLS.py:169-170
+            if (n > 0.0) { mean = s1_[u] / n; var = fmax(s2_[u] / n - mean * mean, 0.0); }
+            if (p.out_mv) { p.out_mv[(size_t)i * 2] = mean; p.out_mv[(size_t)i * 2 + 1] = var; }
+            if (!p.out_action || a == 0 || n0 < (double)p.rp.visited_times_thres ||
+                n < (double)p.rp.min_candidate_visits || mean0 > p.rp.rule_mean_gate)
+                continue;                                                      // RLS.py:141
+            const double z = (mean - mean0) / sqrt(var0 / n0 + var / n);     // RLS.py:144-148
+            if (0.5 * erfc(-z * 0.70710678118654752440) > p.rp.confidence_thres) atomicMin(p.out_action + q, a);   // RLS.py:150-154
         }
     }
     __syncthreads();
     if (p.out_action)
         for (int q = tid; q < p.Q; q += nthr)
             if (__ldcg(p.out_action + q) == 0x7fffffff) p.out_action[q] = 0;
+    if (tid == 0) {
+        p.hdr[0] = 0u;
+        if (p.last_launch) { p.hdr[2] = p.n3_total; p.hdr[1] = p.hdr[1] + 1u; }
+    }
 }
 
 // ---- many queries: a per-dimension bitmap pre-filter ---------------------------------------------------
@@ -233,7 +238,10 @@ __device__ __forceinline__ void box_epilogue(const BoxArgs &p, const int tid, co
 // instructions per dim for all queries at once, the warp leaves as soon as no lane has a candidate left), and
 // the few (row, query) pairs that survive take the exact test as before.  Rows outside the queries' range
 // clamp into the edge bins (conservative); NaN coordinates land in bin 0 and fail the exact test.
-constexpr int kSigBins = 32, kSigMaxQ = 64;
+#ifndef DCARL_SIG_BINS
+#define DCARL_SIG_BINS 32
+#endif
+constexpr int kSigBins = DCARL_SIG_BINS, kSigMaxQ = 64;
 __host__ __device__ inline size_t filter_smem_bytes(int Q, int D) {
     return (size_t)D * kSigBins * sizeof(unsigned long long) + (size_t)D * sizeof(float2) + (size_t)2 * Q * D;
 }
@@ -309,7 +317,8 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
             if (t < n_full) issue(t, s);
         }
 
-    double *bins = p.bins_in_smem ? sbins : p.out;
+    double *gacc = FUSED ? box_fused_accumulator(p, tid, kTileRows) : p.out;
+    double *bins = p.bins_in_smem ? sbins : gacc;
     const double dist_act = p.dist[D];
     long long it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -379,10 +388,10 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
         __syncthreads();
         for (int i = tid; i < nbins * 3; i += kTileRows) {
             const double v = sbins[i];
-            if (v != 0.0) atomicAdd(p.out + i, v);
+            if (v != 0.0) atomicAdd(gacc + i, v);
         }
     }
-    if (FUSED) box_epilogue(p, tid, kTileRows);
+    if (FUSED) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, kTileRows);   // (the tile ring is free now)
 }
 
 // ---- many queries (float32 buffer, 20 observation dims): the bitmap-filtered scan ----------------------------
@@ -390,7 +399,13 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
 // after 8-12 dims), so there is no CTA-wide tile and no CTA barrier in the loop: every WARP streams its own
 // sub-tiles of 32 rows through a private ring (1-D TMA bulk copies of 32 x 84 + 32 x 4 bytes, one mbarrier per
 // stage, lane 0 issues, the 32 lanes wait), warp w of the grid taking sub-tiles w, w + n_warps, ...
-constexpr int kFiltWarps = 8, kFiltStages = 3, kFiltD = 20, kFiltW = kFiltD + 1;
+#ifndef DCARL_FILT_WARPS
+#define DCARL_FILT_WARPS 16
+#endif
+#ifndef DCARL_FILT_STAGES
+#define DCARL_FILT_STAGES 2
+#endif
+constexpr int kFiltWarps = DCARL_FILT_WARPS, kFiltStages = DCARL_FILT_STAGES, kFiltD = 20, kFiltW = kFiltD + 1;
 constexpr int kFiltStageBytes = 32 * kFiltW * 4 + 32 * 4;   // 2816: state rows, then the returns
 
 __host__ __device__ inline size_t box_filter_smem_bytes(int Q, int n_actions, bool bins_in_smem) {
@@ -490,7 +505,8 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
         for (int i = tid; i < nbins * 3; i += NT) sbins[i] = 0.0;
     __syncthreads();
 
-    double *bins = p.bins_in_smem ? sbins : p.out;
+    double *gacc = FUSED ? box_fused_accumulator(p, tid, NT) : p.out;
+    double *bins = p.bins_in_smem ? sbins : gacc;
     const double dist_act = p.dist[D];
     // One row per lane: x = its 20 observation values + the action (shared or global memory), r = its return.
     auto scan_row = [&](const float *x, const float *r, bool valid) {
@@ -559,10 +575,10 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
         __syncthreads();
         for (int i = tid; i < nbins * 3; i += NT) {
             const double v = sbins[i];
-            if (v != 0.0) atomicAdd(p.out + i, v);
+            if (v != 0.0) atomicAdd(gacc + i, v);
         }
     }
-    if (FUSED) box_epilogue(p, tid, NT);
+    if (FUSED) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, NT);   // (the rings are free now)
 }
 
 // moments -> mean/var (+ sentinel) and the act_test pick, one thread per query
@@ -688,7 +704,8 @@ extern "C" int dcarl_box_moments(const void *buf_state, const void *buf_ret, int
         a.hi = reinterpret_cast<unsigned char *>(hi) + (size_t)q0 * D * sp.elem;
         a.dist = dist;
         a.out = out_moments + (size_t)q0 * n_actions * 3;
-        a.queries = nullptr; a.ticket = nullptr; a.out_moments = nullptr; a.out_mv = nullptr; a.out_action = nullptr;
+        a.queries = nullptr; a.hdr = nullptr; a.acc[0] = a.acc[1] = nullptr; a.q0_off = 0; a.n3_total = 0; a.last_launch = 0;
+        a.out_moments = nullptr; a.out_mv = nullptr; a.out_action = nullptr;
         a.rp = dcarl_rls_params{}; a.peers = PeerCtx{};
         const int rc = buf_is_f64 ? launch_scan<double, false>(a, sp, sms, st) : launch_scan<float, false>(a, sp, sms, st);
         if (rc) return rc;
@@ -699,7 +716,8 @@ extern "C" int dcarl_box_moments(const void *buf_state, const void *buf_ret, int
 extern "C" size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions) {
     (void)D;
     if (Q <= 0 || n_actions <= 0) return 0;
-    return (size_t)Q * n_actions * 3 * sizeof(double) + 16;   // accumulator + ticket
+    const size_t half = ((size_t)Q * n_actions * 3 * sizeof(double) + 15) & ~(size_t)15;
+    return 2 * half + 32;   // header {ticket, calls, extent} + two accumulators (+ slack for the split of any ws_bytes)
 }
 
 extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
@@ -720,8 +738,12 @@ extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int b
     if (!ws || ws_bytes < dcarl_box_query_ws(Q, D, n_actions) || ((uintptr_t)ws & 15))
         return bad_arg(14, "workspace too small or misaligned (see dcarl_box_query_ws)");
     cudaStream_t st = (cudaStream_t)stream;
-    double *acc = reinterpret_cast<double *>(ws);
-    unsigned *ticket = reinterpret_cast<unsigned *>(acc + (size_t)Q * n_actions * 3);
+    if ((size_t)Q * n_actions * 3 > 0x7fffffffu) return bad_arg(8, "Q * n_actions too large");
+    // (the halves depend on ws_bytes only: one workspace may serve calls of different shapes)
+    unsigned *hdr = reinterpret_cast<unsigned *>(ws);
+    const size_t half = ((ws_bytes - 16) / 2) & ~(size_t)15;
+    double *acc0 = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ws) + 16);
+    double *acc1 = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ws) + 16 + half);
     ScanPlan sp;
     if (int rc = plan_scan(Q, D, n_actions, buf_is_f64, sp)) return rc;
     PeerCtx pc;
@@ -735,9 +757,12 @@ extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int b
         BoxArgs a;
         a.buf_state = buf_state; a.buf_ret = buf_ret; a.M = M; a.D = D; a.Q = qn; a.n_actions = n_actions;
         a.lo = nullptr; a.hi = nullptr; a.dist = dist;
-        a.out = acc + (size_t)q0 * n_actions * 3;
+        a.out = nullptr;
         a.queries = queries + (size_t)q0 * D;
-        a.ticket = ticket;
+        a.hdr = hdr; a.acc[0] = acc0; a.acc[1] = acc1;
+        a.q0_off = (unsigned)((size_t)q0 * n_actions * 3);
+        a.n3_total = (unsigned)((size_t)Q * n_actions * 3);
+        a.last_launch = q0 + sp.qc >= Q;
         a.out_moments = out_moments + (size_t)q0 * n_actions * 3;
         a.out_mv = out_mean_var ? out_mean_var + (size_t)q0 * n_actions * 2 : nullptr;
         a.out_action = out_action ? out_action + q0 : nullptr;

@@ -200,8 +200,9 @@ int dcarl_sample_returns_philox(const void *q_star, int q_is_f64, uint64_t seed,
  * evaluated in float64; a query point obs (+) a (RLS:91-93) matches the rows whose box contains it.
  * For each of the Q queries (float64 [Q, D]) and each candidate action a in [0, n_actions) writes the
  * raw moments out_moments[q, a, {0,1,2}] = {n, sum R, sum R^2} (float64; zeroed by the call).
- * One streaming pass over the buffer, independent of Q (many queries on a float32 buffer go through a
- * bit-signature pre-filter so that the pass stays close to HBM-bound). */
+ * One streaming pass over the buffer, independent of Q (eight or more queries on a float32 buffer of 20
+ * observation dims go through a per-dimension bitmap pre-filter, 64 queries per pass, so that the pass
+ * stays close to HBM-bound). */
 size_t dcarl_box_moments_ws(int32_t Q, int32_t D, int32_t n_actions);
 int dcarl_box_moments(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
                       const double *dist /* [D+1] */, const double *queries /* [Q, D] */,
@@ -210,8 +211,10 @@ int dcarl_box_moments(const void *buf_state, const void *buf_ret, int buf_is_f64
 /* One act_test query pass as ONE launch (RLS:120-157 for Q observations): thresholds in the kernel's
  * prologue, the scan, and — in the last CTA to finish — the totals, their sum over the ranks that hold the
  * other row shards (peers != NULL and peers->world > 1; see dcarl_peer_ctx), (mean, var) and the pick.
- * ws: dcarl_box_query_ws() bytes, 16-byte aligned, zero-initialised ONCE by the caller; every call
- * leaves it zeroed again (no memset per query).  out_moments [Q, n_actions, 3] holds the totals over all
+ * ws: at least dcarl_box_query_ws() bytes, 16-byte aligned, zero-initialised ONCE by the caller and then
+ * owned by the calls that use it (same pointer and ws_bytes every time; stream-ordered): it holds a call
+ * counter and two accumulators that alternate, each call zeroing the other one for the next call on its way
+ * in (no memset and no copy per query).  out_moments [Q, n_actions, 3] holds the totals over all
  * ranks; out_mean_var / out_action as in dcarl_box_select (each nullable). */
 size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions);
 int dcarl_box_query(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,

@@ -268,7 +268,7 @@ def test_query_graph_is_not_disturbed_by_other_calls_on_the_buffer():
 
 
 def test_fused_query_launch_matches_the_three_step_path():
-    """dcarl_box_query (thresholds + scan + totals + select in one launch, workspace left zeroed) against
+    """dcarl_box_query (thresholds + scan + totals + select in one launch, two alternating accumulators) against
     dcarl_box_moments + dcarl_box_select, including the global-atomics bins, chunked queries, repeated
     calls on one workspace and an empty buffer."""
     from dcarl_b200 import dist as dd
@@ -286,7 +286,9 @@ def test_fused_query_launch_matches_the_three_step_path():
             torch.cuda.synchronize()
             assert torch.equal(fmom[:, :, 0], mom[:, :, 0]) and torch.equal(fpick, pick), (Q, na, rep)
             assert float((fmom - mom).abs().max()) < 1e-9 and float((fmv - mv).abs().max()) < 1e-9
-        assert int(fq.ws.view(torch.int32).abs().sum()) == 0            # accumulator and ticket came back zeroed
+        off = (-fq.ws.data_ptr()) % 16                                      # header {ticket, calls, extent} of the workspace
+        hdr = fq.ws[off:off + 12].view(torch.int32).tolist()
+        assert hdr == [0, 3, Q * na * 3]                                    # ticket back at zero, three calls counted
         ref = _oracle_nmv(vs, ret, centers[:Q], na)
         assert np.array_equal(fmom[:, :, 0].cpu().numpy(), ref[:, :, 0])
     empty = dc.BoxBuffer(20)
@@ -386,8 +388,12 @@ def test_many_queries_on_a_buffer_of_many_tiles_per_cta():
         mom = buf.moments(q, n_actions).cpu().numpy()
         assert np.array_equal(mom[:, :, 0], raw[:, :, 0]) and raw[:, :, 0].sum() > 2000
         assert np.abs(mom[:, :, 1:] - raw[:, :, 1:]).max() < 1e-9
-        fm, _, _ = dd.ShardedBoxQuery(buf, 64, n_actions)(q)
-        assert np.array_equal(fm[:, :, 0].cpu().numpy(), raw[:, :, 0])
+        fq = dd.ShardedBoxQuery(buf, 64, n_actions)
+        for rep in range(3):                                               # the two accumulators alternate between calls
+            fm, _, _ = fq(q)
+            assert np.array_equal(fm[:, :, 0].cpu().numpy(), raw[:, :, 0]), rep
+        fm, _, _ = fq(q[::-1].copy())
+        assert np.array_equal(fm[:, :, 0].cpu().numpy(), raw[::-1, :, 0])
         one = buf.moments(q[:1], n_actions).cpu().numpy()                  # the plain scan agrees
         assert np.array_equal(one[0, :, 0], raw[0, :, 0])
 
