@@ -37,7 +37,7 @@ def config_dict(n_inst, n_steps, world):
     return {"workload": WORKLOAD, "n_inst_per_gpu": n_inst, "n_steps": n_steps, "S": S, "A": A,
             "io": "f32 rows in, f32 value/overall + i32 argmax out; float64 accumulation and bounds",
             "cache": "inputs (983 MB) + outputs (983 MB) per step exceed the 126 MB L2",
-            "parallelism": f"instances sharded, {world} rank(s), one stats all-reduce per step"}
+            "parallelism": f"instances sharded, {world} rank(s), one stats all-reduce per step"}   # (peer-memory sum in the summary kernel when the ranks can map each other)
 
 
 def _cores():
@@ -241,14 +241,29 @@ def run_ours(args):
     plan = dc.StreamPlan(n_inst, n_steps, S, A, r_dtype=torch.float32, out_dtype=torch.float32,
                          want_overall=True, want_stats=True)
     stream = torch.cuda.current_stream()
+    # N > 1: the summary kernel ends with the sum over ranks through peer-mapped memory (one launch, no NCCL call
+    # on the step's critical path); without peer mapping the vector goes through NCCL after the kernel
+    import ctypes as C
+    L = dc._abi.lib()
+    peers = ddist.PeerGroup(ddist.STATS_HEADER + A, None, dev)
+    fused_sum = world > 1 and peers.ctx is not None
+    red = torch.zeros(ddist.STATS_HEADER + A, dtype=torch.float64, device=dev)
 
-    def step():
-        res = plan.run_device(idx, act, R)
-        ddist.allreduce_stats(res.stats)
-        return res
+    def stats_step():
+        if fused_sum:
+            dc._abi.check(L.dcarl_stream_stats_reduce(
+                dc._dev.ptr(plan.value), 0, dc._dev.ptr(plan.overall), dc._dev.ptr(plan.activation_step),
+                dc._dev.ptr(plan.act_hist), n_inst, n_steps, S, A, dc._dev.ptr(red), ddist.STATS_HEADER + A, 0,
+                C.byref(peers.ctx), dc._dev.stream_handle(stream)))
+        else:
+            dc._abi.check(L.dcarl_stream_stats(
+                dc._dev.ptr(plan.value), 0, dc._dev.ptr(plan.overall), dc._dev.ptr(plan.activation_step),
+                dc._dev.ptr(plan.act_hist), n_inst, n_steps, S, A, dc._dev.ptr(red), dc._dev.stream_handle(stream)))
+            ddist.allreduce_stats(red)
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        plan.run_device(idx, act, R)
+        stats_step()
     plan.raise_on_bad_rows()
     sampler = ClockSampler(physical_gpu_index(local))
     ddist.barrier()
@@ -267,10 +282,7 @@ def run_ours(args):
             dc._dev.ptr(plan.overall), dc._dev.ptr(plan.act_hist), dc._dev.ptr(plan.bad_rows),
             dc._dev.ptr(plan.ws), plan._ws_bytes, 0, dc._dev.stream_handle(stream)))
         k_ev[i][1].record(stream)
-        dc._abi.check(dc._abi.lib().dcarl_stream_stats(
-            dc._dev.ptr(plan.value), 0, dc._dev.ptr(plan.overall), dc._dev.ptr(plan.activation_step),
-            dc._dev.ptr(plan.act_hist), n_inst, n_steps, S, A, dc._dev.ptr(plan.stats), dc._dev.stream_handle(stream)))
-        ddist.allreduce_stats(plan.stats)
+        stats_step()
     e1.record(stream)
     torch.cuda.synchronize()
     ddist.barrier()
@@ -292,7 +304,7 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     total_steps = world * n_inst * n_steps
     value = total_steps / (ms_per_step * 1e-3)
-    stats = plan.stats.cpu().numpy()
+    stats = red.cpu().numpy()
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ---------------------
     # The public call is StreamPlan.run_pinned.  Headline: the compact wire format (one-byte keys in, one-byte
@@ -357,7 +369,9 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": ncu_traffic(), "kernel": "k_stream_rows",
                          "kernel_ms": k_ms_max, "algorithmic_bytes_per_step": BYTES_PER_STEP, "peak_source": peak_src},
             "stats_check": {"total_steps": float(stats[4]), "expected": float(total_steps),
-                            "activated_pairs": float(stats[2])},
+                            "activated_pairs": float(stats[2]),
+                            "collective": ("sum over ranks through peer memory at the end of the summary kernel" if fused_sum
+                                           else "NCCL all-reduce after the summary kernel" if world > 1 else "none (one rank)")},
         }
     if rank == 0 and world == 1 and not args.no_cpu:
         out.update(cpu_legs(plan, idx, act, R))

@@ -77,6 +77,13 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
 
+// Index of the highest set bit (0xffffffff for 0): one FLO, where 31 - __clz(x) compiles to three instructions.
+__device__ __forceinline__ unsigned top_bit(unsigned x) {
+    unsigned r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 // Everything the bound needs from the sample count alone: 1/n and c_h/sqrt(n), c_h = scale*sqrt(ln(1/alpha)/2).
 // The row kernel keeps a table of these per CTA (n below the table size: two 16-byte loads replace two
 // 1/sqrt evaluations); every other path builds them on the fly with the same roundings.
@@ -271,6 +278,9 @@ __host__ __device__ inline size_t rows_warp_bytes(int S, int A) {
                + (size_t)A * sizeof(unsigned);                                     // per-warp action histogram
     return (b + 15) & ~(size_t)15;
 }
+// (Tried: a lockstep of the warps of a CTA — every 8 batches a warp that is ahead of the slowest warp of its
+// CTA sleeps, so that all instances of an SM finish together.  0.849 -> 0.866-0.883 ms for every period / lag /
+// sleep tried: the spread of the finish times is not where the time goes.)
 constexpr size_t kRowsCtaFixedBytes = 0;
 constexpr int kRowsMaxWarps = 28;   // 72 registers per thread: 28 resident warps per SM, 7 per scheduler
 
@@ -422,7 +432,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         r.mk &= r.ms;
         m.earlier = r.mk & lt;
         r.n += __popc(m.earlier) + 1u;
-        m.r1 = __shfl_sync(FULL_MASK, m.rin, m.earlier ? (__ffs(m.earlier) - 1) : lane);
+        m.r1 = __shfl_sync(FULL_MASK, m.rin, __ffs(m.earlier) - 1);   // (no peer: lane -1 & 31, the value is not used)
     };
     // the oldest peer (11 % of the rows have one), then a loop for the rows with more (0.7 %)
     auto p1_peers = [&](Mom &m) {
@@ -472,8 +482,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
             const bool T = mine && upd && a == c_g;
             const unsigned tm = __ballot_sync(FULL_MASK, T);
             const unsigned cand = tm & ms & lt;
-            const int jp = cand ? (31 - __clz(cand)) : lane_;
-            const double vp = shfl_f64(v, jp);
+            // (no candidate: the source lane is 0xffffffff & 31 = 31, a valid lane whose value the select below drops)
+            const double vp = shfl_f64(v, (int)top_bit(cand));
             m_prev = cand ? vp : c_ms0;
             const double m_k = T ? v : m_prev;
             // (bitwise on purpose: the compares are evaluated unconditionally, no short-circuit branches)
@@ -854,7 +864,7 @@ static const size_t kMaxSmemPerCta = 227 * 1024;
 // finish early and leave their scheduler under-occupied.  With many waves (config 5, 32768 x 500)
 // small CTAs refill an SM sooner: 4 warps 0.180 ms, 28 warps 0.188 ms.
 static int pick_warps_per_cta(long long n_inst, size_t wb, int sms) {
-    long long fit = (long long)(kMaxSmemPerCta / wb);          // warps whose tables fit one CTA
+    long long fit = (long long)((kMaxSmemPerCta - kRowsCtaFixedBytes) / wb);   // warps whose tables fit one CTA
     if (fit > kRowsMaxWarps) fit = kRowsMaxWarps;
     if (fit < 1) fit = 1;
     if (n_inst <= fit * sms) {                                 // one wave: one CTA per SM
