@@ -87,11 +87,13 @@ struct BoxArgs {
     // accumulators alternate between calls (hdr[1] counts the calls): a call adds into one and zeroes the other
     // for the next call on its way in, spread over all CTAs, so nothing is memset or copied per query.
     const double *queries;     // [Q, D]
-    unsigned *hdr;             // {ticket: CTAs that have flushed their bins, calls, extent: doubles the last call used}
+    unsigned *hdr;             // {ticket: CTAs that have flushed their bins, calls, extent: doubles the last call used,
+                               //  pad, two tickets of k_box_reduce_select, pad, pad}
     double *acc[2];            // the two accumulators (whole workspace halves)
     unsigned q0_off;           // this launch's first accumulator element (queries are chunked over launches)
     unsigned n3_total;         // accumulator elements of the whole call
     int last_launch;           // the last launch of a call advances hdr[1]
+    int epilogue;              // 0: the scan only accumulates (k_box_reduce_select follows)
     double *out_moments;       // [Q, n_actions, 3] totals (summed over ranks when peers.world > 1)
     double *out_mv;            // [Q, n_actions, 2], nullable
     int *out_action;           // [Q], nullable
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
             if (v != 0.0) atomicAdd(gacc + i, v);
         }
     }
-    if (FUSED) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, kTileRows);   // (the tile ring is free now)
+    if (FUSED && p.epilogue) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, kTileRows);   // (the tile ring is free now)
 }
 
 // ---- many queries (float32 buffer, 20 observation dims): the bitmap-filtered scan ----------------------------
@@ -578,7 +580,81 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
             if (v != 0.0) atomicAdd(gacc + i, v);
         }
     }
-    if (FUSED) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, NT);   // (the rings are free now)
+    if (FUSED && p.epilogue) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, NT);   // (the rings are free now)
+}
+
+// ---- row-sharded buffer, many queries: the sum over ranks and the select as a second launch ----------------
+// The fused epilogue is ONE CTA: fine for the 6 KB of a single query, not for 64 x 256 x 3 doubles, which that
+// CTA would push to every peer alone (measured at 2 ranks: the Q = 64 query pass took as long as on one GPU).
+// Here one CTA per query exchanges and sums that query's na x 3 totals through the peer workspace of
+// peer.cuh — same slots, one flag per rank: the last CTA of a rank to have written its slice raises the
+// rank's flag on every peer, every CTA waits for all flags in its own workspace — and runs the query's select.
+// At most 64 CTAs: all resident, so the CTAs of a rank never wait for one that cannot start.
+__global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
+    const int tid = threadIdx.x, q = blockIdx.x, na = p.n_actions, n3q = na * 3;
+    const PeerCtx &c = p.peers;
+    __shared__ unsigned s_e, s_last;
+    __shared__ double s_rule[3];
+    const unsigned calls = p.hdr[1];
+    const double *acc = p.acc[calls & 1u] + p.q0_off + (size_t)q * n3q;
+    if (tid == 0) s_e = *c.epoch + 1u;                    // (bumped by the last CTA to finish, below)
+    __syncthreads();
+    const unsigned e = s_e;
+    const size_t par = e & 1u;
+    // my query's totals into slot [par][my rank] of every rank
+    const size_t slot_off = (par * c.world + c.rank) * (size_t)c.n_max + (size_t)q * n3q;
+    for (int r = 0; r < c.world; ++r) {
+        double *d = c.slots[r] + slot_off;
+        for (int i = tid; i < n3q; i += blockDim.x) d[i] = __ldcg(acc + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(p.hdr + 4, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (s_last) {                                         // every slice of this rank is written: tell the peers
+        __threadfence_system();
+        if (tid < c.world) st_release_sys(c.flags[tid] + par * c.world + c.rank, e);
+    }
+    if (tid < c.world) {
+        const unsigned *f = c.flags[c.rank] + par * c.world + tid;
+        while ((int)(ld_acquire_sys(f) - e) < 0) __nanosleep(20);
+    }
+    __syncthreads();
+    // rank-ordered sum (bit-identical on every rank) -> out_moments
+    const double *mine = c.slots[c.rank] + par * c.world * (size_t)c.n_max + (size_t)q * n3q;
+    double *tot = p.out_moments + (size_t)q * n3q;
+    for (int i = tid; i < n3q; i += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < c.world; ++r) sum += ld_relaxed_sys(mine + (size_t)r * c.n_max + i);
+        tot[i] = sum;
+        if (i < 3) s_rule[i] = sum;
+    }
+    int *pick = p.out_action ? p.out_action + q : nullptr;
+    if (tid == 0 && pick) *pick = 0x7fffffff;
+    __syncthreads();
+    const double n0 = s_rule[0];
+    const double mean0 = n0 > 0.0 ? s_rule[1] / n0 : -1.0;
+    const double var0 = n0 > 0.0 ? fmax(s_rule[2] / n0 - mean0 * mean0, 0.0) : -1.0;
+    for (int a = tid; a < na; a += blockDim.x) {
+        const double n = tot[a * 3];
+        double mean = -1.0, var = -1.0;                                        // RLS.py:169-170
+        if (n > 0.0) { mean = tot[a * 3 + 1] / n; var = fmax(tot[a * 3 + 2] / n - mean * mean, 0.0); }
+        if (p.out_mv) { p.out_mv[((size_t)q * na + a) * 2] = mean; p.out_mv[((size_t)q * na + a) * 2 + 1] = var; }
+        if (!pick || a == 0 || n0 < (double)p.rp.visited_times_thres || n < (double)p.rp.min_candidate_visits ||
+            mean0 > p.rp.rule_mean_gate)
+            continue;                                                          // RLS.py:141
+        const double z = (mean - mean0) / sqrt(var0 / n0 + var / n);         // RLS.py:144-148
+        if (0.5 * erfc(-z * 0.70710678118654752440) > p.rp.confidence_thres) atomicMin(pick, a);   // RLS.py:150-154
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (pick && __ldcg(pick) == 0x7fffffff) *pick = 0;
+        if (atomicAdd(p.hdr + 5, 1u) == gridDim.x - 1u) {   // the last CTA of the launch
+            *c.epoch = e;
+            p.hdr[4] = 0u; p.hdr[5] = 0u;
+            if (p.last_launch) { p.hdr[2] = p.n3_total; p.hdr[1] = calls + 1u; }
+        }
+    }
 }
 
 // moments -> mean/var (+ sentinel) and the act_test pick, one thread per query
@@ -602,6 +678,7 @@ static size_t box_smem_bytes(int Q, int D, int n_actions, bool bins_in_smem, siz
 }
 
 constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSoloEpilogueMax = 4096;   // doubles one CTA sums over the ranks by itself (fused epilogue)
 
 struct ScanPlan {
     int qc;             // queries per launch
@@ -705,6 +782,7 @@ extern "C" int dcarl_box_moments(const void *buf_state, const void *buf_ret, int
         a.dist = dist;
         a.out = out_moments + (size_t)q0 * n_actions * 3;
         a.queries = nullptr; a.hdr = nullptr; a.acc[0] = a.acc[1] = nullptr; a.q0_off = 0; a.n3_total = 0; a.last_launch = 0;
+        a.epilogue = 0;
         a.out_moments = nullptr; a.out_mv = nullptr; a.out_action = nullptr;
         a.rp = dcarl_rls_params{}; a.peers = PeerCtx{};
         const int rc = buf_is_f64 ? launch_scan<double, false>(a, sp, sms, st) : launch_scan<float, false>(a, sp, sms, st);
@@ -717,7 +795,7 @@ extern "C" size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions) {
     (void)D;
     if (Q <= 0 || n_actions <= 0) return 0;
     const size_t half = ((size_t)Q * n_actions * 3 * sizeof(double) + 15) & ~(size_t)15;
-    return 2 * half + 32;   // header {ticket, calls, extent} + two accumulators (+ slack for the split of any ws_bytes)
+    return 2 * half + 48;   // 32-byte header + two accumulators (+ slack for the split of any ws_bytes)
 }
 
 extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
@@ -741,9 +819,9 @@ extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int b
     if ((size_t)Q * n_actions * 3 > 0x7fffffffu) return bad_arg(8, "Q * n_actions too large");
     // (the halves depend on ws_bytes only: one workspace may serve calls of different shapes)
     unsigned *hdr = reinterpret_cast<unsigned *>(ws);
-    const size_t half = ((ws_bytes - 16) / 2) & ~(size_t)15;
-    double *acc0 = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ws) + 16);
-    double *acc1 = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ws) + 16 + half);
+    const size_t half = ((ws_bytes - 32) / 2) & ~(size_t)15;
+    double *acc0 = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ws) + 32);
+    double *acc1 = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ws) + 32 + half);
     ScanPlan sp;
     if (int rc = plan_scan(Q, D, n_actions, buf_is_f64, sp)) return rc;
     PeerCtx pc;
@@ -763,6 +841,9 @@ extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int b
         a.q0_off = (unsigned)((size_t)q0 * n_actions * 3);
         a.n3_total = (unsigned)((size_t)Q * n_actions * 3);
         a.last_launch = q0 + sp.qc >= Q;
+        // many totals on several ranks: the scan only accumulates, a second launch (one CTA per query) sums and selects
+        const bool split = pc.world > 1 && (size_t)qn * n_actions * 3 > kSoloEpilogueMax && qn <= 64;
+        a.epilogue = split ? 0 : 1;
         a.out_moments = out_moments + (size_t)q0 * n_actions * 3;
         a.out_mv = out_mean_var ? out_mean_var + (size_t)q0 * n_actions * 2 : nullptr;
         a.out_action = out_action ? out_action + q0 : nullptr;
@@ -770,6 +851,10 @@ extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int b
         a.peers = pc;
         const int rc = buf_is_f64 ? launch_scan<double, true>(a, sp, sms, st) : launch_scan<float, true>(a, sp, sms, st);
         if (rc) return rc;
+        if (split) {
+            k_box_reduce_select<<<qn, 256, 0, st>>>(a);
+            DCARL_LAUNCH_CHECK("k_box_reduce_select");
+        }
     }
     return 0;
 }

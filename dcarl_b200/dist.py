@@ -199,6 +199,10 @@ class ShardedBoxQuery:
         self.peers = peers if peers is not None else PeerGroup(min(self.Q, 64) * self.na * 3, group, dev)
         if self.world == 1:
             self.path = "one launch: thresholds + scan + totals + select"
+        elif self.peers.ctx is not None and min(self.Q, 64) * self.na * 3 > 4096:
+            # (kSoloEpilogueMax in csrc/box.cu: too many totals for the one CTA of the fused epilogue)
+            self.path = ("two launches: thresholds + scan, then one CTA per query for the peer-memory sum over ranks "
+                         "and the select")
         elif self.peers.ctx is not None:
             self.path = "one launch: thresholds + scan + peer-memory sum over ranks + select"
         else:
