@@ -789,7 +789,14 @@ __global__ void __launch_bounds__(128) k_stream_walk(const StreamArgs p, unsigne
     if (p.bad_rows != nullptr && bad) atomicAdd(p.bad_rows, bad);
 }
 
-// ---- summary statistics (fixed-order float64 reduction, one CTA) -----------------------------
+// ---- summary statistics (fixed-order float64 reduction, one thread-block cluster) ---------------
+// One CTA was fine for the 4096 instances of config 2 (20 us) and the bottleneck of config 5: 131 072 instances
+// x 20 activation steps are 21 MB, ~0.3 ms through one SM — a quarter of the batch.  Now the kStatsCtas CTAs of
+// one cluster take contiguous instance ranges, hand their four partial sums to CTA 0 through distributed shared
+// memory, and CTA 0 adds them in rank order (then the sum over ranks, as before): still one launch, no
+// workspace, and a fixed order of additions for a given n_inst.
+constexpr int kStatsCtas = 8;   // portable cluster size
+
 template <typename OT>
 __global__ void __launch_bounds__(1024) k_stream_stats(const OT *__restrict__ out_value,
                                                         const OT *__restrict__ out_overall,
@@ -799,28 +806,32 @@ __global__ void __launch_bounds__(1024) k_stream_stats(const OT *__restrict__ ou
                                                         double *stats, int width, int accumulate,
                                                         const PeerCtx peers) {
     __shared__ double sh[4][1024];
+    __shared__ double part[kStatsCtas][4];          // CTA 0's copy collects the partial sums of the cluster
     const int t = threadIdx.x;
+    const unsigned cr = cluster_ctarank(), nc = cluster_nctarank();
+    const long long per = (n_inst + nc - 1) / nc;
+    const long long i_lo = min(n_inst, (long long)cr * per), i_hi = min(n_inst, i_lo + per);
     double v = 0.0, o = 0.0, na = 0.0, sa = 0.0;
     if (n_steps > 0) {
         const OT *lv = out_value + n_steps - 1;
         const OT *lo = out_overall ? out_overall + n_steps - 1 : nullptr;
-        for (long long i = t; i < n_inst; i += 4096) {   // four independent loads in flight per array
+        for (long long i = i_lo + t; i < i_hi; i += 4096) {   // four independent loads in flight per array
             OT x[4], y[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const long long ii = i + 1024ll * u;
-                x[u] = ii < n_inst ? lv[ii * n_steps] : OT(0);
-                y[u] = (lo && ii < n_inst) ? lo[ii * n_steps] : OT(0);
+                x[u] = ii < i_hi ? lv[ii * n_steps] : OT(0);
+                y[u] = (lo && ii < i_hi) ? lo[ii * n_steps] : OT(0);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) { v += (double)x[u]; o += (double)y[u]; }
         }
     }
-    const long long n_as = n_inst * S;
-    for (long long i = t; i < n_as; i += 8192) {
+    const long long a_lo = i_lo * S, a_hi = i_hi * S;
+    for (long long i = a_lo + t; i < a_hi; i += 8192) {
         long long st[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const long long ii = i + 1024ll * u; st[u] = ii < n_as ? activation[ii] : -1; }
+        for (int u = 0; u < 8; ++u) { const long long ii = i + 1024ll * u; st[u] = ii < a_hi ? activation[ii] : -1; }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
             if (st[u] != -1) { na += 1.0; sa += (double)st[u]; }
@@ -832,10 +843,13 @@ __global__ void __launch_bounds__(1024) k_stream_stats(const OT *__restrict__ ou
             for (int q = 0; q < 4; ++q) sh[q][t] += sh[q][t + w];
         __syncthreads();
     }
+    if (t < 4) st_shared_cluster(mapa_shared(smem_u32(&part[cr][t]), 0u), sh[t][0]);
+    cluster_sync_all();
+    if (cr != 0) return;
     // this call's vector, zero-padded to `width`, optionally on top of what `stats` holds (mixed batches)
     for (int i = t; i < width; i += 1024) {
         double x = 0.0;
-        if (i < 4) x = sh[i][0];
+        if (i < 4) { for (unsigned r = 0; r < nc; ++r) x += part[r][i]; }
         else if (i == 4) x = (double)n_inst * (double)n_steps;
         else if (i - DCARL_STATS_HEADER < A) x = act_hist ? (double)act_hist[i - DCARL_STATS_HEADER] : 0.0;
         stats[i] = accumulate ? stats[i] + x : x;
@@ -1070,12 +1084,20 @@ extern "C" int dcarl_stream_stats_reduce(const void *out_value, int out_is_f64, 
     cudaStream_t st = (cudaStream_t)stream;
     const long long *as = reinterpret_cast<const long long *>(out_activation_step);
     const unsigned long long *ah = reinterpret_cast<const unsigned long long *>(act_hist);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kStatsCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(kStatsCtas); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int s_ = S, a_ = A, w_ = stats_width, acc_ = accumulate;
+    const long long ni = n_inst, ns = n_steps;
     if (out_is_f64)
-        k_stream_stats<double><<<1, 1024, 0, st>>>((const double *)out_value, (const double *)out_overall, as, ah,
-                                                   n_inst, n_steps, S, A, stats, stats_width, accumulate, pc);
+        DCARL_CUDA(cudaLaunchKernelEx(&cfg, k_stream_stats<double>, (const double *)out_value, (const double *)out_overall,
+                                      as, ah, ni, ns, s_, a_, stats, w_, acc_, pc));
     else
-        k_stream_stats<float><<<1, 1024, 0, st>>>((const float *)out_value, (const float *)out_overall, as, ah,
-                                                  n_inst, n_steps, S, A, stats, stats_width, accumulate, pc);
+        DCARL_CUDA(cudaLaunchKernelEx(&cfg, k_stream_stats<float>, (const float *)out_value, (const float *)out_overall,
+                                      as, ah, ni, ns, s_, a_, stats, w_, acc_, pc));
     DCARL_LAUNCH_CHECK("k_stream_stats");
     return 0;
 }
