@@ -326,36 +326,21 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
 
     const int S = p.S, A = p.A, ncell = S * A;
     StateHot *hot = reinterpret_cast<StateHot *>(smem_raw + kRowsCtaFixedBytes + (size_t)warp * warp_bytes);
-#ifdef DCARL_V_MOM16   // A/B variant: {s1, s2} as one 16-byte record (one LDS.128 / STS.128), the values in their own array
-    double2 *mom2 = reinterpret_cast<double2 *>(hot + S);
-    double *vals = reinterpret_cast<double *>(mom2 + ncell);
-    unsigned *cnt = reinterpret_cast<unsigned *>(vals + ncell);
-#else
     Cell *cells = reinterpret_cast<Cell *>(hot + S);
     unsigned *cnt = reinterpret_cast<unsigned *>(cells + ncell);
-#endif
     int *actstep = reinterpret_cast<int *>(cnt + ncell);       // activation step per state, -1 = not yet (ST1:58)
     int *flushpt = actstep + S;
     unsigned *hist = reinterpret_cast<unsigned *>(flushpt + S);
 
     for (int c = lane; c < ncell; c += 32) {
-#ifdef DCARL_V_MOM16
-        mom2[c] = make_double2(0.0, 0.0); cnt[c] = 0u;
-        vals[c] = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;
-#else
         cells[c].s1 = 0.0; cells[c].s2 = 0.0; cnt[c] = 0u;
         cells[c].val = (c % A == p.rule_act) ? p.prior_rule : p.prior_other;   // ST1:51-53
-#endif
     }
     for (int a = lane; a < A; a += 32) hist[a] = 0u;
     __syncwarp();
     {
         double m0, sec0; int g0;
-#ifdef DCARL_V_MOM16
-        warp_top2(vals, 1, A, m0, g0, sec0);
-#else
         warp_top2(&cells[0].val, 3, A, m0, g0, sec0);
-#endif
         StateHot h0;
         h0.smax = m0; h0.sub2 = pack_bound(runner_up_bound(sec0, m0), (unsigned)g0);
         for (int s = lane; s < S; s += 32) { hot[s] = h0; actstep[s] = -1; flushpt[s] = 0; }
@@ -438,12 +423,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         r.a = a;
         r.kx = in_stream ? s_in * A + a : 0;
         peer_masks(r.s, a, r.ms, r.mk);   // mk = action peers until p1a_peers
-#ifdef DCARL_V_MOM16
-        { const double2 t2 = mom2[r.kx]; m.acc1 = t2.x; m.acc2 = t2.y; }
-#else
         const Cell *cell = cells + r.kx;
         m.acc1 = cell->s1; m.acc2 = cell->s2;
-#endif
         r.n = cnt[r.kx];
     };
     // peers part: the cell mask, the row's sample count, the return of the oldest in-batch peer
@@ -471,12 +452,8 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
         m.acc2 = fma(x, x, m.acc2);
         __syncwarp();   // every lane has read its cell
         if (r.active && (r.mk & gt) == 0) {
-#ifdef DCARL_V_MOM16
-            cnt[r.kx] = r.n; mom2[r.kx] = make_double2(m.acc1, m.acc2);
-#else
             Cell *cell = cells + r.kx;
             cnt[r.kx] = r.n; cell->s1 = m.acc1; cell->s2 = m.acc2;
-#endif
         }
         r.v = cell_value(r.n, m.acc1, m.acc2, r.a == rule, c_h, cap);
     };
@@ -541,11 +518,7 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 o.mprev_out = done ? m_prev : o.mprev_out;
                 o.act_prev = done ? activated : o.act_prev;
             }
-#ifdef DCARL_V_MOM16
-            if (done & upd & ((mk & fin & gt) == 0)) vals[r.kx] = v;
-#else
             if (done & upd & ((mk & fin & gt) == 0)) cells[r.kx].val = v;
-#endif
             const bool last_of_state = done & ((ms & fin & gt) == 0);
             if (last_of_state) sts_f64(sh_a, m_k);
             if (lm != 0) {     // rare: the last finalized row of a lifted state re-centres its bound
@@ -561,23 +534,14 @@ k_stream_rows(const StreamArgs p, const int warps_per_cta, const unsigned warp_b
                 __syncwarp();
                 const int sj = __shfl_sync(FULL_MASK, r.s, j);
                 const unsigned msj = __shfl_sync(FULL_MASK, ms, j);
-#ifdef DCARL_V_MOM16
-                if (lane_ == j && upd) vals[r.kx] = v;
-#else
                 if (lane_ == j && upd) cells[r.kx].val = v;
-#endif
                 __syncwarp();
                 const unsigned opl = bound_payload(lds_f64(hot_sa + (unsigned)sj * (unsigned)sizeof(StateHot) + 8u));
                 const int o_arg = (int)(opl & kArgMask);
                 const bool o_activated = (opl & kActivatedBit) != 0;
                 double mx, second; int arg;
-#ifdef DCARL_V_MOM16
-                if (A <= 32) warp_top2_small(vals + sj * A, 1, A, mx, arg, second);
-                else warp_top2(vals + sj * A, 1, A, mx, arg, second);
-#else
                 if (A <= 32) warp_top2_small(&cells[sj * A].val, 3, A, mx, arg, second);
                 else warp_top2(&cells[sj * A].val, 3, A, mx, arg, second);
-#endif
                 __syncwarp();   // every lane has read the state record and the values before lane j rewrites them
                 // The argmax only ever changes here, so a state can only activate here (ST1:98-99):
                 // between two exact rows "argmax != rule" implies "already activated".
