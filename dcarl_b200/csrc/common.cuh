@@ -25,7 +25,7 @@ int cuda_fail(cudaError_t e, const char *where);
         if (e__ != cudaSuccess) return ::dcarl::cuda_fail(e__, name);       \
     } while (0)
 
-int sm_count();   // cached per device
+int sm_count();   // of the current device (queried per call: the library keeps no state)
 
 // ---- device helpers ----------------------------------------------------------------------
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
