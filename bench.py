@@ -5,8 +5,9 @@ A "step" is one pass of the streaming confidence-bound estimator + argmax select
 batch of synthetic input: BASELINE config 2, "Simulation_2 test_DCARL.py, 4096 parallel scenario
 instances" — 4096 instances x 20 000 rows, S=20 states, A=11 actions, float32 rows in, float32
 value + int32 argmax + float32 overall_value out (24 algorithmic bytes per scenario-step), plus the
-summary-statistics reduction (and, for N > 1, its all-reduce).  N > 1 is weak scaling: every rank
-runs its own 4096 instances, no data-path collective.
+summary-statistics reduction (and, for N > 1, its sum over ranks).  Steps are pipelined over two output sets: the
+summary of step i runs on a side stream beside the stream kernel of step i + 1; the timed region ends when the last
+summary is in.  N > 1 is weak scaling: every rank runs its own 4096 instances, no data-path collective.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [...]                         # the reference's CPU path (port)
@@ -238,33 +239,69 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     n_inst, n_steps = args.n_inst, args.n_steps
     idx, act, R = synth_device(n_inst, n_steps, 1000 + rank, dev)
-    plan = dc.StreamPlan(n_inst, n_steps, S, A, r_dtype=torch.float32, out_dtype=torch.float32,
-                         want_overall=True, want_stats=True)
+    # Two output sets: batch b's summary kernel (+ the sum over ranks) runs on a side stream while batch b + 1's stream
+    # kernel fills the other set ("overlap batch b's all-reduce with batch b+1's kernel via two streams")
+    plans = [dc.StreamPlan(n_inst, n_steps, S, A, r_dtype=torch.float32, out_dtype=torch.float32,
+                           want_overall=True, want_stats=True) for _ in range(2)]
+    plan = plans[0]
     stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev, priority=-1)
     # N > 1: the summary kernel ends with the sum over ranks through peer-mapped memory (one launch, no NCCL call
     # on the step's critical path); without peer mapping the vector goes through NCCL after the kernel
     import ctypes as C
     L = dc._abi.lib()
     peers = ddist.PeerGroup(ddist.STATS_HEADER + A, None, dev)
     fused_sum = world > 1 and peers.ctx is not None
-    red = torch.zeros(ddist.STATS_HEADER + A, dtype=torch.float64, device=dev)
+    reds = [torch.zeros(ddist.STATS_HEADER + A, dtype=torch.float64, device=dev) for _ in range(2)]
 
-    def stats_step():
+    def stats_step(pl, hist_i, red, st):
+        """summary vector of the batch in `pl`'s outputs (+ its action histogram) -> red (summed over ranks), on stream st"""
         if fused_sum:
             dc._abi.check(L.dcarl_stream_stats_reduce(
-                dc._dev.ptr(plan.value), 0, dc._dev.ptr(plan.overall), dc._dev.ptr(plan.activation_step),
-                dc._dev.ptr(plan.act_hist), n_inst, n_steps, S, A, dc._dev.ptr(red), ddist.STATS_HEADER + A, 0,
-                C.byref(peers.ctx), dc._dev.stream_handle(stream)))
+                dc._dev.ptr(pl.value), 0, dc._dev.ptr(pl.overall), dc._dev.ptr(pl.activation_step),
+                dc._dev.ptr(hist_i), n_inst, n_steps, S, A, dc._dev.ptr(red), ddist.STATS_HEADER + A, 0,
+                C.byref(peers.ctx), dc._dev.stream_handle(st)))
         else:
             dc._abi.check(L.dcarl_stream_stats(
-                dc._dev.ptr(plan.value), 0, dc._dev.ptr(plan.overall), dc._dev.ptr(plan.activation_step),
-                dc._dev.ptr(plan.act_hist), n_inst, n_steps, S, A, dc._dev.ptr(red), dc._dev.stream_handle(stream)))
-            ddist.allreduce_stats(red)
+                dc._dev.ptr(pl.value), 0, dc._dev.ptr(pl.overall), dc._dev.ptr(pl.activation_step),
+                dc._dev.ptr(hist_i), n_inst, n_steps, S, A, dc._dev.ptr(red), dc._dev.stream_handle(st)))
+            if world > 1:
+                with torch.cuda.stream(st):
+                    ddist.allreduce_stats(red)
 
-    for _ in range(max(args.warmup, 3)):
-        plan.run_device(idx, act, R)
-        stats_step()
-    plan.raise_on_bad_rows()
+    def run_steps(k, k_ev=None):
+        """k pipelined steps: stream kernel of step i on the main stream, its summary (+ sum over ranks) on the side
+        stream; step i + 2 reuses step i's output set and waits for its summary.  Every step has its own zeroed
+        action histogram (one memset for all of them, outside the loop); bad_rows accumulates over the steps."""
+        done_rows = [torch.cuda.Event() for _ in range(k)]
+        done_stats = [torch.cuda.Event() for _ in range(k)]
+        hist = torch.zeros((k, A), dtype=torch.int64, device=dev)
+        for i in range(k):
+            pl = plans[i & 1]
+            if i >= 2:
+                stream.wait_event(done_stats[i - 2])
+            if k_ev is not None:
+                k_ev[i][0].record(stream)     # events bracket the dominant kernel (k_stream_rows) on the launching stream
+            dc._abi.check(L.dcarl_stream_bounds(
+                dc._dev.ptr(idx), dc._dev.ptr(act), dc._dev.ptr(R), 0, n_inst, n_steps, S, A, pl.params,
+                dc._dev.ptr(pl.value), 0, dc._dev.ptr(pl.act), dc._dev.ptr(pl.activation_step),
+                dc._dev.ptr(pl.overall), dc._dev.ptr(hist[i]), dc._dev.ptr(pl.bad_rows),
+                dc._dev.ptr(pl.ws), pl._ws_bytes, 0, dc._dev.stream_handle(stream)))
+            if k_ev is not None:
+                k_ev[i][1].record(stream)
+            done_rows[i].record(stream)
+            side.wait_event(done_rows[i])
+            stats_step(pl, hist[i], reds[i & 1], side)
+            done_stats[i].record(side)
+        for e in done_stats[-2:]:
+            stream.wait_event(e)              # the timed region ends when the last summaries are in
+
+    for pl in plans:
+        pl.bad_rows.zero_()
+    run_steps(max(args.warmup, 3))
+    torch.cuda.synchronize()
+    for pl in plans:
+        pl.raise_on_bad_rows()
     sampler = ClockSampler(physical_gpu_index(local))
     ddist.barrier()
     torch.cuda.synchronize()
@@ -272,17 +309,7 @@ def run_ours(args):
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(args.steps):
-        # events bracket the dominant kernel (k_stream_rows) on the launching stream
-        plan.act_hist.zero_(); plan.bad_rows.zero_()
-        k_ev[i][0].record(stream)
-        dc._abi.check(dc._abi.lib().dcarl_stream_bounds(
-            dc._dev.ptr(idx), dc._dev.ptr(act), dc._dev.ptr(R), 0, n_inst, n_steps, S, A, plan.params,
-            dc._dev.ptr(plan.value), 0, dc._dev.ptr(plan.act), dc._dev.ptr(plan.activation_step),
-            dc._dev.ptr(plan.overall), dc._dev.ptr(plan.act_hist), dc._dev.ptr(plan.bad_rows),
-            dc._dev.ptr(plan.ws), plan._ws_bytes, 0, dc._dev.stream_handle(stream)))
-        k_ev[i][1].record(stream)
-        stats_step()
+    run_steps(args.steps, k_ev)
     e1.record(stream)
     torch.cuda.synchronize()
     ddist.barrier()
@@ -304,7 +331,7 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     total_steps = world * n_inst * n_steps
     value = total_steps / (ms_per_step * 1e-3)
-    stats = red.cpu().numpy()
+    stats = reds[(args.steps - 1) & 1].cpu().numpy()
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ---------------------
     # The public call is StreamPlan.run_pinned.  Headline: the compact wire format (one-byte keys in, one-byte
@@ -371,13 +398,15 @@ def run_ours(args):
             "stats_check": {"total_steps": float(stats[4]), "expected": float(total_steps),
                             "activated_pairs": float(stats[2]),
                             "collective": ("sum over ranks through peer memory at the end of the summary kernel" if fused_sum
-                                           else "NCCL all-reduce after the summary kernel" if world > 1 else "none (one rank)")},
+                                           else "NCCL all-reduce after the summary kernel" if world > 1 else "none (one rank)"),
+                            "pipeline": "summary (+ sum over ranks) of step i on a side stream beside the stream kernel of "
+                                        "step i + 1 (two output sets)"},
         }
     if rank == 0 and world == 1 and not args.no_cpu:
         out.update(cpu_legs(plan, idx, act, R))
     # BASELINE configs 4 and 5 at this world size (every rank takes part; rank 0 reports)
     del idx, act, R
-    plan = None
+    plan = plans = None
     torch.cuda.empty_cache()
     if not args.no_configs:
         peak = measured_peak()[0]

@@ -1087,8 +1087,11 @@ extern "C" int dcarl_stream_stats_reduce(const void *out_value, int out_is_f64, 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kStatsCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(kStatsCtas); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    // a small batch (config 2: 4096 instances, 0.7 MB) stays ONE CTA: it then fits beside the next batch's stream
+    // kernel (147 CTAs on 148 SMs) when the caller pipelines batches over two streams
+    const unsigned ctas = n_inst >= 16384 ? kStatsCtas : 1;
+    attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int s_ = S, a_ = A, w_ = stats_width, acc_ = accumulate;
     const long long ni = n_inst, ns = n_steps;
