@@ -19,6 +19,8 @@
 // a thread reads "its" row from shared memory (pitch D+1 = 21 words: conflict free).
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "peer.cuh"
 
@@ -511,7 +513,11 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     double *bins = p.bins_in_smem ? sbins : gacc;
     const double dist_act = p.dist[D];
     // One row per lane: x = its 20 observation values + the action (shared or global memory), r = its return.
-    auto scan_row = [&](const float *x, const float *r, bool valid) {
+    // 32 rows, one per lane: rows0 = the first row's 20 observation values + action (shared or global memory, pitch W),
+    // rets0 = its return.  TAIL: lanes past the end of the buffer are not valid and must not load.
+    auto scan_rows = [&](auto tail_tag, const float *rows0, const float *rets0, bool valid) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const float *x = rows0 + lane * W;
         // candidates: the AND of the row's table entries, all queries at once, four dims per round; the warp
         // leaves as soon as no lane has a candidate left (most rows are out after two or three rounds)
         unsigned long long surv = valid ? ~0ull : 0ull;
@@ -523,36 +529,46 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int d = 4 * g + u;
-                    m[u] = stab[d * kSigBins + sig_bin(x[d], sgeo[d])];
+                    const float xv = TAIL ? (valid ? x[d] : 0.f) : x[d];
+                    m[u] = stab[d * kSigBins + sig_bin(xv, sgeo[d])];
                 }
                 surv &= (m[0] & m[1]) & (m[2] & m[3]);
                 alive = __any_sync(FULL_MASK, surv != 0ull);
             }
         }
         if (!alive) return;
-        // the few surviving (row, query) pairs take the exact test, each lane on its own pairs: hits are
-        // rare with many queries, so they go to the bins one atomic triple at a time
-        while (surv) {
-            const int q = __ffsll((long long)surv) - 1;
-            surv &= surv - 1ull;
-            const float *l = slo + q * D, *h = shi + q * D;
-            bool ok = true;
-#pragma unroll 4
-            for (int d = 0; d < D; ++d) { const float v = x[d]; ok = ok && (v >= l[d]) && (v <= h[d]); }
-            if (!ok) continue;
-            // the stored action picks the candidate(s): s_act - dist <= a <= s_act + dist in float64
-            const double sa = (double)x[D];
-            const double alo = sa - dist_act, ahi = sa + dist_act;
-            if (!(alo == alo) || !(ahi == ahi)) continue;
-            const int a0 = (int)fmax(ceil(alo), 0.0), a1 = (int)fmin(floor(ahi), (double)(p.n_actions - 1));
-            const double rr = (double)*r;
-            for (int a = a0; a <= a1; ++a)
-                if (alo <= (double)a && (double)a <= ahi) {
-                    double *b = bins + ((size_t)q * p.n_actions + a) * 3;
-                    atomicAdd(b + 0, 1.0);
-                    atomicAdd(b + 1, rr);
-                    atomicAdd(b + 2, rr * rr);
-                }
+        // The few surviving (row, query) pairs take the exact test, the WARP on one pair at a time with one
+        // observation dim per lane (a lane walking its own pairs through 20 dims kept the other 31 lanes idle:
+        // that loop was 30 % of the kernel's instructions).  Hits are rare with many queries: lane 0 adds them
+        // to the bins one atomic triple at a time.
+        unsigned have = __ballot_sync(FULL_MASK, surv != 0ull);
+        while (have) {                                      // warp-uniform loops
+            const int src = __ffs(have) - 1;
+            have &= have - 1u;
+            unsigned long long sv = __shfl_sync(FULL_MASK, surv, src);
+            const float *xs = rows0 + src * W;
+            const float xd = lane < D ? xs[lane] : 0.f;
+            while (sv) {
+                const int q = __ffsll((long long)sv) - 1;
+                sv &= sv - 1ull;
+                bool in = true;
+                if (lane < D) in = (xd >= slo[q * D + lane]) && (xd <= shi[q * D + lane]);
+                if (!__all_sync(FULL_MASK, in) || lane != 0) continue;
+                // the stored action picks the candidate(s): s_act - dist <= a <= s_act + dist in float64
+                const double sa = (double)xs[D];
+                const double alo = sa - dist_act, ahi = sa + dist_act;
+                if (!(alo == alo) || !(ahi == ahi)) continue;
+                const int a0 = (int)fmax(ceil(alo), 0.0), a1 = (int)fmin(floor(ahi), (double)(p.n_actions - 1));
+                const double rr = (double)rets0[src];
+                for (int a = a0; a <= a1; ++a)
+                    if (alo <= (double)a && (double)a <= ahi) {
+                        double *b = bins + ((size_t)q * p.n_actions + a) * 3;
+                        atomicAdd(b + 0, 1.0);
+                        atomicAdd(b + 1, rr);
+                        atomicAdd(b + 2, rr * rr);
+                    }
+            }
+            __syncwarp();
         }
     };
 
@@ -561,18 +577,14 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
         const int stage = (int)(it % kFiltStages);
         const float *ts = reinterpret_cast<const float *>(ring + (size_t)stage * kFiltStageBytes);
         mbar_wait(&full[stage], (unsigned)((it / kFiltStages) & 1));
-        scan_row(ts + lane * W, ts + 32 * W + lane, true);
+        scan_rows(std::false_type{}, ts, ts + 32 * W, true);
         __syncwarp();                                       // every lane is done with the stage
         const long long nt = sub + (long long)kFiltStages * n_warps;
         if (lane == 0 && nt < n_sub) issue(nt, stage);
     }
     // the last M % 32 rows, straight from global memory, by the warp whose turn it would be
-    if ((p.M & 31) != 0 && w0 == n_sub % n_warps) {
-        const long long row = n_sub * 32 + lane;
-        const bool valid = row < p.M;
-        const long long rr = valid ? row : p.M - 1;
-        scan_row(gstate + rr * W, gret + rr, valid);
-    }
+    if ((p.M & 31) != 0 && w0 == n_sub % n_warps)
+        scan_rows(std::true_type{}, gstate + n_sub * 32 * W, gret + n_sub * 32, n_sub * 32 + lane < p.M);
     if (p.bins_in_smem) {
         __syncthreads();
         for (int i = tid; i < nbins * 3; i += NT) {

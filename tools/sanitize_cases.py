@@ -23,6 +23,10 @@ for (n_inst, n_steps, S, A, kw) in [(9, 700, 20, 11, {}), (5, 333, 1, 30, {}), (
     for variant in (0, 1):
         res = dc.stream_bounds(idx, act, R, S, A, dc.Params(**kw), variant=variant, want_stats=True)
         compare_stream(res, ref, value_tol=1e-9)
+# the summary kernel as a cluster of 8 CTAs (>= 16384 instances)
+idx, act, R = synth_streams(16400, 40, 20, 11, seed=5, r_dtype=np.float32)
+res = dc.stream_bounds(idx, act, R, 20, 11, want_stats=True)
+assert res.stats[4] == 16400 * 40 and res.stats[5:].sum() == 16400 * 40
 print("stream ok")
 rng = np.random.default_rng(0)
 dist = dc.VISITED_STATE_DIST[0]
@@ -37,6 +41,20 @@ for Q in (1, 7):
     assert np.array_equal(n, ref[:, :, 0])
 run = buf.query_graph(1, 8)
 run(vs[:1, :20])
+# many queries: the bitmap-filtered scan (unfused and as the one-launch query, repeated: the accumulators alternate),
+# the float64 storage mode, more queries than one filtered launch takes
+from dcarl_b200 import dist as dd  # noqa: E402
+q64 = np.vstack([vs[:60, :20], vs[:6, :20] + 1e3])
+ref = cport.box_raw(vs.astype(np.float32), ret.astype(np.float32), dist, q64, 8)
+assert np.array_equal(buf.moments(q64, 8).cpu().numpy()[:, :, 0], ref[:, :, 0])
+fq = dd.ShardedBoxQuery(buf, 64, 8)
+for _ in range(3):
+    assert np.array_equal(fq(q64[:64])[0].cpu().numpy()[:, :, 0], ref[:64, :, 0])
+fq = dd.ShardedBoxQuery(buf, 64, 40)                       # 64 x 40 bins: global atomics
+assert np.array_equal(fq(q64[:64])[0].cpu().numpy()[:, :8, 0], ref[:64, :, 0])
+b64 = dc.BoxBuffer(20, dtype=torch.float64)
+b64.append(vs, ret)
+assert np.array_equal(b64.moments(q64[:9], 8).cpu().numpy()[:, :, 0], cport.box_raw(vs, ret, dist, q64[:9], 8)[:, :, 0])
 print("box ok")
 x = [rng.normal(0, 50, n) for n in (1, 17, 300, 5000)]
 got = dc.bounds_batch(x)
