@@ -595,49 +595,57 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     if (FUSED && p.epilogue) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, NT);   // (the rings are free now)
 }
 
-// ---- row-sharded buffer, many queries: the sum over ranks and the select as a second launch ----------------
-// The fused epilogue is ONE CTA: fine for the 6 KB of a single query, not for 64 x 256 x 3 doubles, which that
-// CTA would push to every peer alone (measured at 2 ranks: the Q = 64 query pass took as long as on one GPU).
-// Here one CTA per query exchanges and sums that query's na x 3 totals through the peer workspace of
+// ---- many queries: the sum over ranks and the select as a second launch -----------------------------------
+// The fused epilogue is ONE CTA: fine for the 6 KB of a single query, not for 64 x 256 x 3 doubles — alone it
+// spent 40 us on the (mean, var, pick) of 16 384 pairs (a quarter of the fused Q = 64 pass), and on row shards it
+// would push all of them to every peer (measured at 2 ranks: the pass took as long as on one GPU).
+// Here one CTA per query runs the query's select, after — on row shards — exchanging and summing that query's
+// na x 3 totals through the peer workspace of
 // peer.cuh — same slots, one flag per rank: the last CTA of a rank to have written its slice raises the
 // rank's flag on every peer, every CTA waits for all flags in its own workspace — and runs the query's select.
 // At most 64 CTAs: all resident, so the CTAs of a rank never wait for one that cannot start.
 __global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
     const int tid = threadIdx.x, q = blockIdx.x, na = p.n_actions, n3q = na * 3;
     const PeerCtx &c = p.peers;
+    const bool solo = c.world <= 1;
     __shared__ unsigned s_e, s_last;
     __shared__ double s_rule[3];
     const unsigned calls = p.hdr[1];
     const double *acc = p.acc[calls & 1u] + p.q0_off + (size_t)q * n3q;
-    if (tid == 0) s_e = *c.epoch + 1u;                    // (bumped by the last CTA to finish, below)
-    __syncthreads();
-    const unsigned e = s_e;
-    const size_t par = e & 1u;
-    // my query's totals into slot [par][my rank] of every rank
-    const size_t slot_off = (par * c.world + c.rank) * (size_t)c.n_max + (size_t)q * n3q;
-    for (int r = 0; r < c.world; ++r) {
-        double *d = c.slots[r] + slot_off;
-        for (int i = tid; i < n3q; i += blockDim.x) d[i] = __ldcg(acc + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(p.hdr + 4, 1u) == gridDim.x - 1u;
-    __syncthreads();
-    if (s_last) {                                         // every slice of this rank is written: tell the peers
+    unsigned e = 0;
+    size_t par = 0;
+    if (!solo) {
+        if (tid == 0) s_e = *c.epoch + 1u;                // (bumped by the last CTA to finish, below)
+        __syncthreads();
+        e = s_e;
+        par = e & 1u;
+        // my query's totals into slot [par][my rank] of every rank
+        const size_t slot_off = (par * c.world + c.rank) * (size_t)c.n_max + (size_t)q * n3q;
+        for (int r = 0; r < c.world; ++r) {
+            double *d = c.slots[r] + slot_off;
+            for (int i = tid; i < n3q; i += blockDim.x) d[i] = __ldcg(acc + i);
+        }
         __threadfence_system();
-        if (tid < c.world) st_release_sys(c.flags[tid] + par * c.world + c.rank, e);
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(p.hdr + 4, 1u) == gridDim.x - 1u;
+        __syncthreads();
+        if (s_last) {                                     // every slice of this rank is written: tell the peers
+            __threadfence_system();
+            if (tid < c.world) st_release_sys(c.flags[tid] + par * c.world + c.rank, e);
+        }
+        if (tid < c.world) {
+            const unsigned *f = c.flags[c.rank] + par * c.world + tid;
+            while ((int)(ld_acquire_sys(f) - e) < 0) __nanosleep(20);
+        }
+        __syncthreads();
     }
-    if (tid < c.world) {
-        const unsigned *f = c.flags[c.rank] + par * c.world + tid;
-        while ((int)(ld_acquire_sys(f) - e) < 0) __nanosleep(20);
-    }
-    __syncthreads();
-    // rank-ordered sum (bit-identical on every rank) -> out_moments
-    const double *mine = c.slots[c.rank] + par * c.world * (size_t)c.n_max + (size_t)q * n3q;
+    // the totals (on row shards the rank-ordered sum: bit-identical on every rank) -> out_moments
+    const double *mine = solo ? nullptr : c.slots[c.rank] + par * c.world * (size_t)c.n_max + (size_t)q * n3q;
     double *tot = p.out_moments + (size_t)q * n3q;
     for (int i = tid; i < n3q; i += blockDim.x) {
         double sum = 0.0;
-        for (int r = 0; r < c.world; ++r) sum += ld_relaxed_sys(mine + (size_t)r * c.n_max + i);
+        if (solo) sum = __ldcg(acc + i);
+        else for (int r = 0; r < c.world; ++r) sum += ld_relaxed_sys(mine + (size_t)r * c.n_max + i);
         tot[i] = sum;
         if (i < 3) s_rule[i] = sum;
     }
@@ -662,7 +670,7 @@ __global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
     if (tid == 0) {
         if (pick && __ldcg(pick) == 0x7fffffff) *pick = 0;
         if (atomicAdd(p.hdr + 5, 1u) == gridDim.x - 1u) {   // the last CTA of the launch
-            *c.epoch = e;
+            if (!solo) *c.epoch = e;
             p.hdr[4] = 0u; p.hdr[5] = 0u;
             if (p.last_launch) { p.hdr[2] = p.n3_total; p.hdr[1] = calls + 1u; }
         }
@@ -853,8 +861,8 @@ extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int b
         a.q0_off = (unsigned)((size_t)q0 * n_actions * 3);
         a.n3_total = (unsigned)((size_t)Q * n_actions * 3);
         a.last_launch = q0 + sp.qc >= Q;
-        // many totals on several ranks: the scan only accumulates, a second launch (one CTA per query) sums and selects
-        const bool split = pc.world > 1 && (size_t)qn * n_actions * 3 > kSoloEpilogueMax && qn <= 64;
+        // many totals: the scan only accumulates, a second launch (one CTA per query) sums over the ranks and selects
+        const bool split = (size_t)qn * n_actions * 3 > kSoloEpilogueMax && qn <= 64;
         a.epilogue = split ? 0 : 1;
         a.out_moments = out_moments + (size_t)q0 * n_actions * 3;
         a.out_mv = out_mean_var ? out_mean_var + (size_t)q0 * n_actions * 2 : nullptr;

@@ -197,10 +197,12 @@ class ShardedBoxQuery:
         L = _abi.lib()
         self.ws = torch.zeros(int(L.dcarl_box_query_ws(self.Q, buf.D, self.na)) + 16, dtype=torch.uint8, device=dev)
         self.peers = peers if peers is not None else PeerGroup(min(self.Q, 64) * self.na * 3, group, dev)
-        if self.world == 1:
+        many = min(self.Q, 64) * self.na * 3 > 4096          # (kSoloEpilogueMax in csrc/box.cu: too much for the fused epilogue's one CTA)
+        if self.world == 1 and many:
+            self.path = "two launches: thresholds + scan, then one CTA per query for the select"
+        elif self.world == 1:
             self.path = "one launch: thresholds + scan + totals + select"
-        elif self.peers.ctx is not None and min(self.Q, 64) * self.na * 3 > 4096:
-            # (kSoloEpilogueMax in csrc/box.cu: too many totals for the one CTA of the fused epilogue)
+        elif self.peers.ctx is not None and many:
             self.path = ("two launches: thresholds + scan, then one CTA per query for the peer-memory sum over ranks "
                          "and the select")
         elif self.peers.ctx is not None:
