@@ -37,6 +37,10 @@ __device__ __forceinline__ float next_up(float x) { return nextafterf(x, CUDART_
 __device__ __forceinline__ float next_dn(float x) { return nextafterf(x, -CUDART_INF_F); }
 __device__ __forceinline__ double next_up(double x) { return nextafter(x, CUDART_INF); }
 __device__ __forceinline__ double next_dn(double x) { return nextafter(x, -CUDART_INF); }
+__device__ __forceinline__ float narrow_dn(float v) { return v; }
+__device__ __forceinline__ float narrow_up(float v) { return v; }
+__device__ __forceinline__ float narrow_dn(double v) { return __double2float_rd(v); }
+__device__ __forceinline__ float narrow_up(double v) { return __double2float_ru(v); }
 __device__ __forceinline__ void round_dn_up(double v, float &dn, float &up) { dn = __double2float_rd(v); up = __double2float_ru(v); }
 __device__ __forceinline__ void round_dn_up(double v, double &dn, double &up) { dn = v; up = v; }
 
@@ -410,10 +414,10 @@ __global__ void __launch_bounds__(kTileRows) k_box_moments(const BoxArgs p) {
 #define DCARL_FILT_STAGES 2
 #endif
 constexpr int kFiltWarps = DCARL_FILT_WARPS, kFiltStages = DCARL_FILT_STAGES, kFiltD = 20, kFiltW = kFiltD + 1;
-constexpr int kFiltStageBytes = 32 * kFiltW * 4 + 32 * 4;   // 2816: state rows, then the returns
+template <typename BT> constexpr int filt_stage_bytes() { return 32 * kFiltW * (int)sizeof(BT) + 32 * (int)sizeof(BT); }   // float32: 2816 (state rows, then the returns)
 
-__host__ __device__ inline size_t box_filter_smem_bytes(int Q, int n_actions, bool bins_in_smem) {
-    size_t off = (size_t)kFiltWarps * kFiltStages * kFiltStageBytes + (size_t)2 * Q * kFiltD * sizeof(float);
+__host__ __device__ inline size_t box_filter_smem_bytes(int Q, int n_actions, bool bins_in_smem, size_t elem) {
+    size_t off = (size_t)kFiltWarps * kFiltStages * 32 * (kFiltW + 1) * elem + (size_t)2 * Q * kFiltD * elem;
     off = (off + 15) & ~(size_t)15;
     off += filter_smem_bytes(Q, kFiltD);
     off = (off + 15) & ~(size_t)15;
@@ -422,16 +426,17 @@ __host__ __device__ inline size_t box_filter_smem_bytes(int Q, int n_actions, bo
     return off;
 }
 
-template <bool FUSED>
+template <typename BT, bool FUSED>
 __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p) {
+    constexpr int kFiltStageBytes = filt_stage_bytes<BT>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int D = kFiltD, W = kFiltW, NT = kFiltWarps * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // layout: [warps x stages x {32 rows, 32 returns}][lo Q*D][hi Q*D][tables][bins][mbarriers]
     unsigned char *ring = smem_raw + (size_t)warp * kFiltStages * kFiltStageBytes;
-    float *slo = reinterpret_cast<float *>(smem_raw + (size_t)kFiltWarps * kFiltStages * kFiltStageBytes);
-    float *shi = slo + p.Q * D;
-    size_t off = (size_t)kFiltWarps * kFiltStages * kFiltStageBytes + (size_t)2 * p.Q * D * sizeof(float);
+    BT *slo = reinterpret_cast<BT *>(smem_raw + (size_t)kFiltWarps * kFiltStages * kFiltStageBytes);
+    BT *shi = slo + p.Q * D;
+    size_t off = (size_t)kFiltWarps * kFiltStages * kFiltStageBytes + (size_t)2 * p.Q * D * sizeof(BT);
     off = (off + 15) & ~(size_t)15;
     // per (dim, bin) the set of queries whose interval overlaps the bin; per dim {scale, offset} of the bin
     // function; scratch: the first / last bin of every (query, dim) interval
@@ -446,9 +451,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + off) + warp * kFiltStages;
 
     if (FUSED) {
-        for (int i = tid; i < p.Q * D; i += NT) box_thresholds<float>(p.queries[i], p.dist[i % D], slo[i], shi[i]);
+        for (int i = tid; i < p.Q * D; i += NT) box_thresholds<BT>(p.queries[i], p.dist[i % D], slo[i], shi[i]);
     } else {
-        const float *glo = reinterpret_cast<const float *>(p.lo), *ghi = reinterpret_cast<const float *>(p.hi);
+        const BT *glo = reinterpret_cast<const BT *>(p.lo), *ghi = reinterpret_cast<const BT *>(p.hi);
         for (int i = tid; i < p.Q * D; i += NT) { slo[i] = glo[i]; shi[i] = ghi[i]; }
     }
     if (lane == 0) {
@@ -457,16 +462,16 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     }
     __syncthreads();
     // this warp's first sub-tiles are on their way while the CTA builds the tables
-    const float *gstate = reinterpret_cast<const float *>(p.buf_state);
-    const float *gret = reinterpret_cast<const float *>(p.buf_ret);
+    const BT *gstate = reinterpret_cast<const BT *>(p.buf_state);
+    const BT *gret = reinterpret_cast<const BT *>(p.buf_ret);
     const long long n_sub = p.M / 32;                       // complete sub-tiles (TMA-loadable)
     const long long n_warps = (long long)gridDim.x * kFiltWarps;
     const long long w0 = (long long)blockIdx.x * kFiltWarps + warp;
     auto issue = [&](long long sub, int stage) {            // lane 0 only
         unsigned char *dst = ring + (size_t)stage * kFiltStageBytes;
         mbar_arrive_expect_tx(&full[stage], (unsigned)kFiltStageBytes);
-        tma_load_1d(dst, gstate + sub * 32 * W, 32 * W * 4, &full[stage]);
-        tma_load_1d(dst + 32 * W * 4, gret + sub * 32, 32 * 4, &full[stage]);
+        tma_load_1d(dst, gstate + sub * 32 * W, 32 * W * (int)sizeof(BT), &full[stage]);
+        tma_load_1d(dst + 32 * W * sizeof(BT), gret + sub * 32, 32 * (int)sizeof(BT), &full[stage]);
     };
     if (lane == 0)
         for (int s = 0; s < kFiltStages; ++s) {
@@ -477,7 +482,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     if (tid < D) {
         float gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
         for (int q = 0; q < p.Q; ++q) {
-            const float l = slo[q * D + tid], h = shi[q * D + tid];
+            const float l = narrow_dn(slo[q * D + tid]), h = narrow_up(shi[q * D + tid]);
             if (l <= h) { gmin = fminf(gmin, l); gmax = fmaxf(gmax, h); }
         }
         float scale = 0.f;
@@ -489,9 +494,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     // first / last bin of every interval (the same bin function as the rows': monotone in the stored value,
     // so a value inside [l, h] lands in [bin(l), bin(h)]); an empty interval gets first > last
     for (int i = tid; i < p.Q * D; i += NT) {
-        const float l = slo[i], h = shi[i];
+        const float l = narrow_dn(slo[i]), h = narrow_up(shi[i]);   // (float64 thresholds: rounded outwards)
         const float2 g = sgeo[i % D];
-        const bool some = l <= h;
+        const bool some = slo[i] <= shi[i];
         sb01[2 * i] = (unsigned char)(some ? sig_bin(l, g) : 1);
         sb01[2 * i + 1] = (unsigned char)(some ? sig_bin(h, g) : 0);
     }
@@ -515,9 +520,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     // One row per lane: x = its 20 observation values + the action (shared or global memory), r = its return.
     // 32 rows, one per lane: rows0 = the first row's 20 observation values + action (shared or global memory, pitch W),
     // rets0 = its return.  TAIL: lanes past the end of the buffer are not valid and must not load.
-    auto scan_rows = [&](auto tail_tag, const float *rows0, const float *rets0, bool valid) {
+    auto scan_rows = [&](auto tail_tag, const BT *rows0, const BT *rets0, bool valid) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        const float *x = rows0 + lane * W;
+        const BT *x = rows0 + lane * W;
         // candidates: the AND of the row's table entries, all queries at once, four dims per round; the warp
         // leaves as soon as no lane has a candidate left (most rows are out after two or three rounds)
         unsigned long long surv = valid ? ~0ull : 0ull;
@@ -529,7 +534,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int d = 4 * g + u;
-                    const float xv = TAIL ? (valid ? x[d] : 0.f) : x[d];
+                    // (a float64 value is rounded to nearest for its bin: monotone, and inside the outward-rounded interval
+                    //  of every query whose exact interval holds it)
+                    const float xv = (float)(TAIL ? (valid ? x[d] : BT(0)) : x[d]);
                     m[u] = stab[d * kSigBins + sig_bin(xv, sgeo[d])];
                 }
                 surv &= (m[0] & m[1]) & (m[2] & m[3]);
@@ -546,8 +553,8 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
             const int src = __ffs(have) - 1;
             have &= have - 1u;
             unsigned long long sv = __shfl_sync(FULL_MASK, surv, src);
-            const float *xs = rows0 + src * W;
-            const float xd = lane < D ? xs[lane] : 0.f;
+            const BT *xs = rows0 + src * W;
+            const BT xd = lane < D ? xs[lane] : BT(0);
             while (sv) {
                 const int q = __ffsll((long long)sv) - 1;
                 sv &= sv - 1ull;
@@ -575,7 +582,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     long long it = 0;
     for (long long sub = w0; sub < n_sub; sub += n_warps, ++it) {
         const int stage = (int)(it % kFiltStages);
-        const float *ts = reinterpret_cast<const float *>(ring + (size_t)stage * kFiltStageBytes);
+        const BT *ts = reinterpret_cast<const BT *>(ring + (size_t)stage * kFiltStageBytes);
         mbar_wait(&full[stage], (unsigned)((it / kFiltStages) & 1));
         scan_rows(std::false_type{}, ts, ts + 32 * W, true);
         __syncwarp();                                       // every lane is done with the stage
@@ -709,11 +716,11 @@ struct ScanPlan {
 // float32 buffer of 20 observation dims go through the bitmap filter, at most kSigMaxQ per launch.
 static int plan_scan(int Q, int D, int n_actions, int buf_is_f64, ScanPlan &sp) {
     sp.elem = buf_is_f64 ? sizeof(double) : sizeof(float);
-    sp.filt = !buf_is_f64 && D == kFiltD && Q >= 8;
+    sp.filt = D == kFiltD && Q >= 8;
     sp.qc = Q;
     if (sp.filt) {
         if (sp.qc > kSigMaxQ) sp.qc = kSigMaxQ;
-        return 0;                                           // 64 queries always fit (box_filter_smem_bytes: 86 KB)
+        return 0;                                           // 64 queries always fit (box_filter_smem_bytes: 108 KB float32, 209 KB float64)
     }
     while (sp.qc > 1 && box_smem_bytes(sp.qc, D, n_actions, false, sp.elem) > kSmemBudget) sp.qc = (sp.qc + 1) / 2;
     if (box_smem_bytes(sp.qc, D, n_actions, false, sp.elem) > kSmemBudget) return bad_arg(4, "D too large for the tile ring");
@@ -732,16 +739,14 @@ static int launch_scan(BoxArgs &a, const ScanPlan &sp, int sms, cudaStream_t st)
         if (grid > units) grid = units;
         return (unsigned)(grid < 1 ? 1 : grid);             // (an empty shard still takes part in the reduction)
     };
-    if constexpr (sizeof(BT) == 4) {
-        if (sp.filt && qn >= 8) {
-            a.bins_in_smem = (qn * na <= kMaxSmemBins) && box_filter_smem_bytes(qn, na, true) <= kSmemBudget;
-            const size_t smem = box_filter_smem_bytes(qn, na, a.bins_in_smem);
-            const unsigned grid = grid_of(smem, (a.M / 32 + kFiltWarps - 1) / kFiltWarps);
-            DCARL_CUDA(cudaFuncSetAttribute(k_box_filter<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_box_filter<FUSED><<<grid, kFiltWarps * 32, smem, st>>>(a);
-            DCARL_LAUNCH_CHECK("k_box_filter");
-            return 0;
-        }
+    if (sp.filt && qn >= 8) {
+        a.bins_in_smem = (qn * na <= kMaxSmemBins) && box_filter_smem_bytes(qn, na, true, sizeof(BT)) <= kSmemBudget;
+        const size_t smem = box_filter_smem_bytes(qn, na, a.bins_in_smem, sizeof(BT));
+        const unsigned grid = grid_of(smem, (a.M / 32 + kFiltWarps - 1) / kFiltWarps);
+        DCARL_CUDA(cudaFuncSetAttribute(k_box_filter<BT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_box_filter<BT, FUSED><<<grid, kFiltWarps * 32, smem, st>>>(a);
+        DCARL_LAUNCH_CHECK("k_box_filter");
+        return 0;
     }
     a.bins_in_smem = (qn * na <= kMaxSmemBins) && box_smem_bytes(qn, D, na, true, sp.elem) <= kSmemBudget;
     const size_t smem = box_smem_bytes(qn, D, na, a.bins_in_smem, sp.elem);

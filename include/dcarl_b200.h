@@ -200,9 +200,9 @@ int dcarl_sample_returns_philox(const void *q_star, int q_is_f64, uint64_t seed,
  * evaluated in float64; a query point obs (+) a (RLS:91-93) matches the rows whose box contains it.
  * For each of the Q queries (float64 [Q, D]) and each candidate action a in [0, n_actions) writes the
  * raw moments out_moments[q, a, {0,1,2}] = {n, sum R, sum R^2} (float64; zeroed by the call).
- * One streaming pass over the buffer, independent of Q (eight or more queries on a float32 buffer of 20
- * observation dims go through a per-dimension bitmap pre-filter, 64 queries per pass, so that the pass
- * stays close to HBM-bound). */
+ * One streaming pass over the buffer, independent of Q (eight or more queries on a buffer of 20 observation dims go
+ * through a per-dimension bitmap pre-filter, 64 queries per pass, so that the pass stays close to
+ * HBM-bound). */
 size_t dcarl_box_moments_ws(int32_t Q, int32_t D, int32_t n_actions);
 int dcarl_box_moments(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
                       const double *dist /* [D+1] */, const double *queries /* [Q, D] */,

@@ -59,10 +59,10 @@ def test_register_budget_of_the_row_kernel():
 
 
 def test_box_scan_uses_bulk_copies():
-    for sym in ("k_box_momentsIfLi20ELb1E", "k_box_momentsIdLi20ELb1E", "k_box_filterILb1E"):
-        sass = [s for _, s in _sass(sym)]                        # float32 fused, float64 fused, float32 fused + filter
+    for sym in ("k_box_momentsIfLi20ELb1E", "k_box_momentsIdLi20ELb1E", "k_box_filterIfLb1E", "k_box_filterIdLb1E"):
+        sass = [s for _, s in _sass(sym)]                        # float32 fused, float64 fused, the filtered scans
         assert any("UBLKCP" in s for s in sass)                  # 1-D TMA tile loads
         assert any("SYNCS" in s for s in sass)                   # mbarrier arrive / wait
-    filt = [s for _, s in _sass("k_box_filterILb0E")]
+    filt = [s for _, s in _sass("k_box_filterIfLb0E")]
     assert sum("LDS.64" in s for s in filt) >= 40                # one bin-geometry and one bitmap-table entry per observation dim
     assert any("VOTE" in s for s in filt)                        # the warp-wide early exit
