@@ -136,6 +136,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, unsigned rank) {
 __device__ __forceinline__ void st_shared_cluster(uint32_t addr, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
+// Every CTA of the cluster has started (required before the first access to another CTA's shared memory).
+__device__ __forceinline__ void cluster_arrive_wait_entered() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

@@ -843,6 +843,7 @@ __global__ void __launch_bounds__(1024) k_stream_stats(const OT *__restrict__ ou
             for (int q = 0; q < 4; ++q) sh[q][t] += sh[q][t + w];
         __syncthreads();
     }
+    if (nc > 1) cluster_arrive_wait_entered();   // (distributed shared memory may only be touched once its CTA runs)
     if (t < 4) st_shared_cluster(mapa_shared(smem_u32(&part[cr][t]), 0u), sh[t][0]);
     cluster_sync_all();
     if (cr != 0) return;
