@@ -47,6 +47,7 @@ class BoxBuffer:
         self._state = torch.empty((capacity, self.D + 1), dtype=dtype, device=self.device)
         self._ret = torch.empty((capacity,), dtype=dtype, device=self.device)
         self._ws = None
+        self._qws = None            # workspace of the one-launch query (query()): call counter + two accumulators
         self._index_dim = None      # see build_index(): rows [0, _index_rows) are sorted by this dim
         self._index_rows = 0
         self._index_col = None
@@ -150,10 +151,11 @@ class BoxBuffer:
         self.last_scanned_rows += (row_hi - row_lo) if Q else 0
 
     def query_fused(self, q, n_actions, rls_params, ws, out, peer_ctx=None, stream=None):
-        """One launch for a whole act_test query pass (dcarl_box_query): q float64 CUDA [Q, D]; ws a
-        zero-initialised uint8 CUDA tensor of dcarl_box_query_ws() bytes that the kernel leaves zeroed;
-        out = (moments [Q, A, 3], mean_var [Q, A, 2], action int32 [Q]) CUDA tensors; peer_ctx sums the
-        moments over the ranks holding the other row shards."""
+        """One launch for a whole act_test query pass (dcarl_box_query; a second small launch when there are many
+        (query, action) pairs): q float64 CUDA [Q, D]; ws a uint8 CUDA tensor of at least dcarl_box_query_ws() + 16
+        bytes, zero-initialised ONCE and then owned by the calls that use it (it holds the call counter and the two
+        alternating accumulators); out = (moments [Q, A, 3], mean_var [Q, A, 2], action int32 [Q]) CUDA tensors;
+        peer_ctx sums the moments over the ranks holding the other row shards."""
         mom, mv, pick = out
         L = _abi.lib()
         with torch.cuda.device(self.device):
@@ -252,8 +254,20 @@ class BoxBuffer:
         (if built) for up to 8 queries, the single full pass otherwise."""
         q = np.asarray(obs, np.float64).reshape(-1, self.D)
         use_index = self._index_dim is not None and len(q) <= 8
-        mom = self.moments_indexed(q, n_actions) if use_index else self.moments(q, n_actions)
-        mv, pick = self.select(mom, rls_params)
+        if use_index:
+            mom = self.moments_indexed(q, n_actions)
+            mv, pick = self.select(mom, rls_params)
+        else:                                   # thresholds + scan + totals + select in one launch
+            qd = _dev.as_device(q, torch.float64, self.device).contiguous()
+            Q = qd.shape[0]
+            need = int(_abi.lib().dcarl_box_query_ws(Q, self.D, n_actions)) + 16
+            if self._qws is None or self._qws.numel() < need:
+                self._qws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+            mom = torch.empty((Q, n_actions, 3), dtype=torch.float64, device=self.device)
+            mv = torch.empty((Q, n_actions, 2), dtype=torch.float64, device=self.device)
+            pick = torch.empty((Q,), dtype=torch.int32, device=self.device)
+            if Q:
+                self.query_fused(qd, n_actions, rls_params, self._qws, (mom, mv, pick))
         mom_h, mv_h = mom.cpu().numpy(), mv.cpu().numpy()
         return mom_h[:, :, 0], mv_h[:, :, 0], mv_h[:, :, 1], pick.cpu().numpy()
 
