@@ -615,12 +615,13 @@ __global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
     const int tid = threadIdx.x, q = blockIdx.x, na = p.n_actions, n3q = na * 3;
     const PeerCtx &c = p.peers;
     const bool solo = c.world <= 1;
-    __shared__ unsigned s_e, s_last;
+    __shared__ unsigned s_e, s_last, s_lost;
     __shared__ double s_rule[3];
     const unsigned calls = p.hdr[1];
     const double *acc = p.acc[calls & 1u] + p.q0_off + (size_t)q * n3q;
     unsigned e = 0;
     size_t par = 0;
+    if (tid == 0) s_lost = 0u;
     if (!solo) {
         if (tid == 0) s_e = *c.epoch + 1u;                // (bumped by the last CTA to finish, below)
         __syncthreads();
@@ -640,12 +641,10 @@ __global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
             __threadfence_system();
             if (tid < c.world) st_release_sys(c.flags[tid] + par * c.world + c.rank, e);
         }
-        if (tid < c.world) {
-            const unsigned *f = c.flags[c.rank] + par * c.world + tid;
-            while ((int)(ld_acquire_sys(f) - e) < 0) __nanosleep(20);
-        }
+        if (tid < c.world && !peer_wait_flag(c.flags[c.rank] + par * c.world + tid, e)) s_lost = 1u;
         __syncthreads();
     }
+    const bool lost = !solo && s_lost != 0u;              // a peer never arrived: NaN totals (see peer_wait_flag)
     // the totals (on row shards the rank-ordered sum: bit-identical on every rank) -> out_moments
     const double *mine = solo ? nullptr : c.slots[c.rank] + par * c.world * (size_t)c.n_max + (size_t)q * n3q;
     double *tot = p.out_moments + (size_t)q * n3q;
@@ -653,6 +652,7 @@ __global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
         double sum = 0.0;
         if (solo) sum = __ldcg(acc + i);
         else for (int r = 0; r < c.world; ++r) sum += ld_relaxed_sys(mine + (size_t)r * c.n_max + i);
+        if (lost) sum = __longlong_as_double(0x7ff8000000000000ll);
         tot[i] = sum;
         if (i < 3) s_rule[i] = sum;
     }

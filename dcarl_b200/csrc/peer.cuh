@@ -35,11 +35,29 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
     return v;
 }
 
+// Waits until *f has reached call `e`; gives up after kPeerWaitNs (a rank that died would otherwise leave the others
+// spinning for ever, and the GPU with them).  Returns false on a timeout.
+constexpr unsigned long long kPeerWaitNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ bool peer_wait_flag(const unsigned *f, unsigned e) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0; (int)(ld_acquire_sys(f) - e) < 0; ++spins) {
+        __nanosleep(20);
+        if ((spins & 1023u) == 1023u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > kPeerWaitNs) return false;
+        }
+    }
+    return true;
+}
+
 // All threads of ONE CTA call this.  src: this rank's n doubles (global or shared memory);
 // dst: global, receives the rank-ordered sum (may alias src).
 __device__ __forceinline__ void peer_allreduce_cta(const double *src, double *dst, int n, const PeerCtx &c) {
-    __shared__ unsigned s_epoch;
+    __shared__ unsigned s_epoch, s_lost;
     const int tid = threadIdx.x, nth = blockDim.x;
+    if (tid == 0) s_lost = 0u;
     if (tid == 0) { s_epoch = *c.epoch + 1u; *c.epoch = s_epoch; }
     __syncthreads();
     const unsigned e = s_epoch;
@@ -51,16 +69,14 @@ __device__ __forceinline__ void peer_allreduce_cta(const double *src, double *ds
     __threadfence_system();
     __syncthreads();
     if (tid < c.world) st_release_sys(c.flags[tid] + par * c.world + c.rank, e);
-    if (tid < c.world) {
-        const unsigned *f = c.flags[c.rank] + par * c.world + tid;
-        while ((int)(ld_acquire_sys(f) - e) < 0) __nanosleep(20);
-    }
+    if (tid < c.world && !peer_wait_flag(c.flags[c.rank] + par * c.world + tid, e)) s_lost = 1u;
     __syncthreads();
     const double *mine = c.slots[c.rank] + par * c.world * (size_t)c.n_max;
+    const bool lost = s_lost != 0u;             // a peer never arrived: NaN, so that nothing downstream looks valid
     for (int i = tid; i < n; i += nth) {
         double sum = 0.0;
         for (int r = 0; r < c.world; ++r) sum += ld_relaxed_sys(mine + (size_t)r * c.n_max + i);
-        dst[i] = sum;
+        dst[i] = lost ? __longlong_as_double(0x7ff8000000000000ll) : sum;
     }
 }
 
