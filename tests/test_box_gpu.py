@@ -298,6 +298,23 @@ def test_fused_query_launch_matches_the_three_step_path():
     assert float(fmom.abs().sum()) == 0 and bool((fmv == -1).all()) and bool((fpick == 0).all())
 
 
+def test_one_workspace_serves_queries_of_changing_shape():
+    """BoxBuffer.query keeps ONE workspace for the one-launch query path: the two accumulators alternate between
+    calls and a call zeroes what the previous call used of the other one, whatever the shapes were (more queries
+    than one launch takes, one query, more candidate actions, back to many)."""
+    rng = np.random.default_rng(41)
+    centers, vs, ret = _clustered(rng, n_centers=80, n_actions=12, max_rows=25)
+    buf = dc.BoxBuffer(20)
+    buf.append(vs, ret)
+    for Q, na in ((70, 8), (1, 8), (3, 40), (70, 12), (2, 256), (70, 8), (1, 12)):
+        q = centers[:Q] + rng.uniform(-0.2, 0.2, (Q, 20)) * DIST[:20]
+        n, mean, var, pick = buf.query(q, na)
+        ref = _oracle_nmv(vs, ret, q, na)
+        assert np.array_equal(n, ref[:, :, 0]), (Q, na)
+        assert np.abs(mean - ref[:, :, 1]).max() < 1e-9 and np.abs(var - ref[:, :, 2]).max() < 1e-9
+        assert np.array_equal(pick, cport.box_select(ref)), (Q, na)
+
+
 def test_stats_chain_of_a_mixed_batch():
     """dcarl_stream_stats_reduce: zero-padded width and accumulation across the shapes of a mixed batch."""
     from dcarl_b200 import dist as dd
