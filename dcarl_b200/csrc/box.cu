@@ -13,10 +13,17 @@
 // k_box_prepare finds them (exact float64 predicate, +-1 ulp walk); the scan then needs
 // two float32 compares per dim and still reproduces the float64 decision bit for bit.
 //
-// Data movement: the AoS buffer [M, D+1] float32 is staged tile by tile into shared
-// memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, 4-stage ring), so global
-// reads are whole 16-byte-aligned contiguous tiles regardless of the odd row pitch, and
-// a thread reads "its" row from shared memory (pitch D+1 = 21 words: conflict free).
+// Data movement: the AoS buffer [M, D+1] (float32, or float64 in the reference-parity storage
+// mode) is staged tile by tile into shared memory with 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier), so global reads are whole 16-byte-aligned contiguous tiles regardless of the odd
+// row pitch, and a thread reads "its" row from shared memory (pitch D+1 = 21 words: conflict free).
+//
+// Kernels: k_box_moments (one or a few queries: CTA-wide 256-row tiles, 4-stage ring),
+// k_box_filter (eight or more queries: per-dimension bitmap pre-filter, per-warp 32-row rings),
+// both also as the whole act_test query in one launch (FUSED: thresholds in the prologue, two
+// alternating accumulators, totals + sum over ranks + select in the last CTA's epilogue);
+// k_box_reduce_select (many queries: sum over ranks + select, one CTA per query);
+// k_box_prepare / k_box_select (the unfused thresholds / select).
 #include <math_constants.h>
 
 #include <type_traits>

@@ -12,9 +12,10 @@ import dcarl_b200 as dc
 
 dev = torch.device("cuda:0")
 idx, act, R = bench.synth_device(bench.N_INST, bench.N_STEPS, 1000, dev)
-plan = dc.StreamPlan(bench.N_INST, bench.N_STEPS, bench.S, bench.A)
+key = torch.uint8 if os.environ.get("KEYS", "u8") == "u8" else torch.int32     # KEYS=i32: the int32 wire format
+plan = dc.StreamPlan(bench.N_INST, bench.N_STEPS, bench.S, bench.A, key_dtype=key)
 pin = plan.pinned()
-pin["idx"].copy_(idx); pin["act"].copy_(act); pin["R"].copy_(R)
+pin["idx"].copy_(idx.to(key)); pin["act"].copy_(act.to(key)); pin["R"].copy_(R)
 torch.cuda.synchronize()
 for chunks in [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "4,8,16,32").split(",")]:
     plan.run_pinned(chunks=chunks)
