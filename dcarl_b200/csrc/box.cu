@@ -628,10 +628,9 @@ __global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
     const double *acc = p.acc[calls & 1u] + p.q0_off + (size_t)q * n3q;
     unsigned e = 0;
     size_t par = 0;
-    if (tid == 0) s_lost = 0u;
+    if (tid == 0) { s_lost = 0u; s_e = solo ? 0u : *c.epoch + 1u; }   // (the epoch is bumped by the last CTA to finish, below)
+    __syncthreads();
     if (!solo) {
-        if (tid == 0) s_e = *c.epoch + 1u;                // (bumped by the last CTA to finish, below)
-        __syncthreads();
         e = s_e;
         par = e & 1u;
         // my query's totals into slot [par][my rank] of every rank
