@@ -480,6 +480,7 @@ def secondary(dev, peak):
                          "episodes_per_s": ne / (ms * 1e-3), "note": "96 B per episode: latency/compute bound, no roofline fraction"}
     del s0, ra, zs, zr, ac
     out["frenet_plan"] = frenet_leg(dev)
+    out["closed_loop"] = closed_loop_leg(dev)
     return out
 
 
@@ -683,6 +684,76 @@ def synth_frenet(n, n_paths, seed, max_obs=4):
     obs = np.concatenate([pos, (v * np.cos(yaw))[..., None], (v * np.sin(yaw))[..., None], yaw[..., None]], 2)
     n_obs = rng.integers(0, max_obs + 1, n).astype(np.int32)
     return knots, off, pid, start, ego, obs, n_obs
+
+
+def closed_loop_leg(dev):
+    """The collector's loop the metric is named after (dqn_value_collect.py:86-145 under the reward / termination
+    rules of TestScenario_Town03.py:403-422), on the device from end to end for a batch of scenarios: planner tick
+    (10 candidates) -> episode return of every candidate against constant-velocity obstacles -> (state, action,
+    return) rows into the box buffer -> box-kernel confidence of every scenario's state -> act_test pick.  Stage
+    times from CUDA events; the returns of a sample are checked against the oracle's restatement of those lines."""
+    import torch
+    import dcarl_b200 as dc
+    from oracle import pyref
+    n, n_paths = 32768, 64
+    knots, off, pid, start, ego_xy, obs, n_obs = synth_frenet(n, n_paths, 6000, max_obs=3)
+    rng = np.random.default_rng(6001)
+    ang, v = rng.uniform(-np.pi, np.pi, n), rng.uniform(3, 9, n)
+    ego = np.c_[ego_xy, v * np.cos(ang), v * np.sin(ang), v]
+    routes = dc.Routes(knots)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    d_pid, d_ego, d_obs, d_nobs = t(pid, torch.int32), t(ego, torch.float64), t(obs, torch.float64), t(n_obs, torch.int32)
+    rp = dc.rollout_params(pass_y=float(np.median(ego[:, 1])))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    reps, stage = 3, np.zeros(4)
+    for rep in range(reps + 1):                        # the first pass is the warm-up
+        buf = dc.BoxBuffer(20, capacity=n * 11)
+        torch.cuda.synchronize()
+        ev[0].record()
+        st0 = dc.frenet_start(routes, d_pid, d_ego)
+        exy = d_ego[:, :2].contiguous()
+        plan = dc.frenet_plan(routes, d_pid, st0, exy, d_obs, d_nobs, want_paths=True)
+        ev[1].record()
+        ret, steps, term = dc.rollout_candidates(plan, exy, d_obs, d_nobs, rp)
+        ev[2].record()
+        A = ret.shape[1]
+        st = torch.zeros((n, 20), dtype=torch.float64, device=dev)
+        st[:, 0:4] = d_ego[:, 0:4]
+        st[:, 4] = torch.atan2(d_ego[:, 3], d_ego[:, 2])
+        present = (torch.arange(3, device=dev)[None, :] < d_nobs[:, None]).to(torch.float64)
+        st[:, 5:20] = (d_obs[:, :3, :] * present[:, :, None]).reshape(n, 15)
+        rows = torch.cat([st[:, None, :].expand(n, A, 20),
+                          torch.arange(A, dtype=torch.float64, device=dev)[None, :, None].expand(n, A, 1)], 2)
+        buf.append(rows.reshape(n * A, 21), ret.reshape(n * A))
+        ev[3].record()
+        mom = buf.moments(st, A)                       # n queries against the n x A rows just recorded: ONE launch,
+        mv, pick = buf.select(mom)                     # a CTA per chunk of 64 queries scans the (L2-resident) buffer
+        ev[4].record()
+        torch.cuda.synchronize()
+        if rep:
+            stage += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        del buf
+    stage /= reps
+    # parity of the rollout on a sample: returns / steps / termination codes of every action
+    paths, nv, cost = plan.paths.cpu().numpy(), plan.n_valid.cpu().numpy(), plan.cost.cpu().numpy()
+    g_ret, g_steps, g_term = ret.cpu().numpy(), steps.cpu().numpy(), term.cpu().numpy()
+    bad, max_err = 0, 0.0
+    sample = rng.choice(n, 64, replace=False)
+    for i in sample:
+        want = pyref.rollout_candidates(paths[i], nv[i], cost[i], ego_xy[i], [tuple(x) for x in obs[i, :n_obs[i]]], considered=4,
+                                        move_gap=1.0, n_pred=15, dt=0.3, radius=1.0, pass_y=rp.pass_y, stay_thres=rp.stay_thres)
+        bad += int([w[1] for w in want] != g_steps[i].tolist()) + int([w[2] for w in want] != g_term[i].tolist())
+        max_err = max(max_err, float(np.abs(np.array([w[0] for w in want]) - g_ret[i]).max()))
+    total = float(stage.sum())
+    return {"scenarios": n, "actions_per_scenario": int(A), "ms": {"planner_tick": stage[0], "candidate_rollout": stage[1],
+                                                                  "record_rows": stage[2], "confidence_and_pick": stage[3], "total": total},
+            "scenarios_per_s": n / (total * 1e-3), "candidate_episodes_per_s": n * int(A) / (stage[1] * 1e-3),
+            "kinematic_steps_per_s": float(g_steps.sum()) / (stage[1] * 1e-3), "rows_recorded": n * int(A),
+            "picks_other_than_rule": int((pick != 0).sum()),
+            "parity": {"sampled_scenarios": len(sample), "step_or_termination_mismatches": bad, "max_abs_return_error": max_err,
+                       "oracle": "oracle/pyref.py rollout_candidates (restates dqn_value_collect.py:86-145, TestScenario_Town03.py:403-422, predict.py:52-59)"},
+            "note": "confidence_and_pick answers the n queries against the n x A rows just recorded in one filtered launch "
+                    "(n / 64 query chunks, a CTA per chunk over the L2-resident buffer) + the select"}
 
 
 def frenet_leg(dev):

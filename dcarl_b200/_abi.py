@@ -108,6 +108,7 @@ SIGNATURES = {
                                            _vp, _vp, _vp, _int, _vp]),
     "dcarl_box_moments_ws": (_sz, [_i32, _i32, _i32]),
     "dcarl_box_moments": (_int, [_vp, _vp, _int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "dcarl_box_moments_ranges": (_int, [_vp, _vp, _int, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "dcarl_box_query_ws": (_sz, [_i32, _i32, _i32]),
     "dcarl_box_query": (_int, [_vp, _vp, _int, _i64, _i32, _vp, _vp, _i32, _i32, C.POINTER(RlsParams), _vp, _vp, _vp,
                                _vp, _sz, C.POINTER(PeerCtx), _vp]),

@@ -107,6 +107,10 @@ struct BoxArgs {
     unsigned n3_total;         // accumulator elements of the whole call
     int last_launch;           // the last launch of a call advances hdr[1]
     int epilogue;              // 0: the scan only accumulates (k_box_reduce_select follows)
+    // unfused k_box_filter on a small (L2-resident) buffer with more queries than one pass takes: n_chunks > 1 —
+    // every CTA takes whole chunks of Q queries (lo / hi / out advance by chunk; the last chunk holds
+    // q_total - (n_chunks - 1) * Q queries) and scans the WHOLE buffer for each, in ONE launch
+    int n_chunks, q_total;
     double *out_moments;       // [Q, n_actions, 3] totals (summed over ranks when peers.world > 1)
     double *out_mv;            // [Q, n_actions, 2], nullable
     int *out_action;           // [Q], nullable
@@ -453,42 +457,51 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     off += filter_smem_bytes(p.Q, D);
     off = (off + 15) & ~(size_t)15;
     double *sbins = reinterpret_cast<double *>(smem_raw + off);
-    const int nbins = p.Q * p.n_actions;
-    off += p.bins_in_smem ? (size_t)nbins * 3 * sizeof(double) : 0;
+    off += p.bins_in_smem ? (size_t)p.Q * p.n_actions * 3 * sizeof(double) : 0;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + off) + warp * kFiltStages;
 
-    if (FUSED) {
-        for (int i = tid; i < p.Q * D; i += NT) box_thresholds<BT>(p.queries[i], p.dist[i % D], slo[i], shi[i]);
-    } else {
-        const BT *glo = reinterpret_cast<const BT *>(p.lo), *ghi = reinterpret_cast<const BT *>(p.hi);
-        for (int i = tid; i < p.Q * D; i += NT) { slo[i] = glo[i]; shi[i] = ghi[i]; }
-    }
     if (lane == 0) {
         for (int s = 0; s < kFiltStages; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    // this warp's first sub-tiles are on their way while the CTA builds the tables
     const BT *gstate = reinterpret_cast<const BT *>(p.buf_state);
     const BT *gret = reinterpret_cast<const BT *>(p.buf_ret);
     const long long n_sub = p.M / 32;                       // complete sub-tiles (TMA-loadable)
-    const long long n_warps = (long long)gridDim.x * kFiltWarps;
-    const long long w0 = (long long)blockIdx.x * kFiltWarps + warp;
+    // One chunk of queries for the whole grid (the warps of all CTAs share the buffer's sub-tiles), or — many
+    // chunks on a small buffer — whole chunks per CTA (its 16 warps share all sub-tiles, the buffer comes from L2).
+    const int n_chunks = FUSED ? 1 : p.n_chunks;
+    const bool per_cta = n_chunks > 1;
+    const long long n_warps = per_cta ? kFiltWarps : (long long)gridDim.x * kFiltWarps;
+    const long long w0 = per_cta ? warp : (long long)blockIdx.x * kFiltWarps + warp;
     auto issue = [&](long long sub, int stage) {            // lane 0 only
         unsigned char *dst = ring + (size_t)stage * kFiltStageBytes;
         mbar_arrive_expect_tx(&full[stage], (unsigned)kFiltStageBytes);
         tma_load_1d(dst, gstate + sub * 32 * W, 32 * W * (int)sizeof(BT), &full[stage]);
         tma_load_1d(dst + 32 * W * sizeof(BT), gret + sub * 32, 32 * (int)sizeof(BT), &full[stage]);
     };
+    double *gacc = nullptr;
+    long long it = 0;                                       // sub-tiles this warp has taken so far (all chunks): ring position
+    for (int chunk = per_cta ? (int)blockIdx.x : 0; chunk < n_chunks; chunk += per_cta ? (int)gridDim.x : 1) {
+    const int Qn = per_cta ? min(p.Q, p.q_total - chunk * p.Q) : p.Q;
+    const int nbins = Qn * p.n_actions;
+    if (FUSED) {
+        for (int i = tid; i < Qn * D; i += NT) box_thresholds<BT>(p.queries[i], p.dist[i % D], slo[i], shi[i]);
+    } else {
+        const BT *glo = reinterpret_cast<const BT *>(p.lo) + (size_t)chunk * p.Q * D;
+        const BT *ghi = reinterpret_cast<const BT *>(p.hi) + (size_t)chunk * p.Q * D;
+        for (int i = tid; i < Qn * D; i += NT) { slo[i] = glo[i]; shi[i] = ghi[i]; }
+    }
+    __syncthreads();
+    // this warp's first sub-tiles are on their way while the CTA builds the tables
     if (lane == 0)
         for (int s = 0; s < kFiltStages; ++s) {
             const long long t = w0 + (long long)s * n_warps;
-            if (t < n_sub) issue(t, s);
+            if (t < n_sub) issue(t, (int)((it + s) % kFiltStages));
         }
     // bin geometry: the range of the finite thresholds of all queries, per dim
     if (tid < D) {
         float gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
-        for (int q = 0; q < p.Q; ++q) {
+        for (int q = 0; q < Qn; ++q) {
             const float l = narrow_dn(slo[q * D + tid]), h = narrow_up(shi[q * D + tid]);
             if (l <= h) { gmin = fminf(gmin, l); gmax = fmaxf(gmax, h); }
         }
@@ -500,7 +513,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     __syncthreads();
     // first / last bin of every interval (the same bin function as the rows': monotone in the stored value,
     // so a value inside [l, h] lands in [bin(l), bin(h)]); an empty interval gets first > last
-    for (int i = tid; i < p.Q * D; i += NT) {
+    for (int i = tid; i < Qn * D; i += NT) {
         const float l = narrow_dn(slo[i]), h = narrow_up(shi[i]);   // (float64 thresholds: rounded outwards)
         const float2 g = sgeo[i % D];
         const bool some = slo[i] <= shi[i];
@@ -511,7 +524,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
     for (int e = tid; e < D * kSigBins; e += NT) {
         const int d = e / kSigBins, b = e % kSigBins;
         unsigned long long m = 0ull;
-        for (int q = 0; q < p.Q; ++q) {
+        for (int q = 0; q < Qn; ++q) {
             const int i = q * D + d;
             m |= (unsigned long long)((int)sb01[2 * i] <= b && b <= (int)sb01[2 * i + 1]) << q;
         }
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
         for (int i = tid; i < nbins * 3; i += NT) sbins[i] = 0.0;
     __syncthreads();
 
-    double *gacc = FUSED ? box_fused_accumulator(p, tid, NT) : p.out;
+    gacc = FUSED ? box_fused_accumulator(p, tid, NT) : p.out + (size_t)chunk * p.Q * p.n_actions * 3;
     double *bins = p.bins_in_smem ? sbins : gacc;
     const double dist_act = p.dist[D];
     // One row per lane: x = its 20 observation values + the action (shared or global memory), r = its return.
@@ -586,7 +599,6 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
         }
     };
 
-    long long it = 0;
     for (long long sub = w0; sub < n_sub; sub += n_warps, ++it) {
         const int stage = (int)(it % kFiltStages);
         const BT *ts = reinterpret_cast<const BT *>(ring + (size_t)stage * kFiltStageBytes);
@@ -606,6 +618,8 @@ __global__ void __launch_bounds__(kFiltWarps * 32) k_box_filter(const BoxArgs p)
             if (v != 0.0) atomicAdd(gacc + i, v);
         }
     }
+    __syncthreads();                                        // (many chunks: the tables are rebuilt for the next one)
+    }   // chunk
     if (FUSED && p.epilogue) box_epilogue(p, gacc, reinterpret_cast<double *>(smem_raw), tid, NT);   // (the rings are free now)
 }
 
@@ -687,6 +701,79 @@ __global__ void __launch_bounds__(256) k_box_reduce_select(const BoxArgs p) {
             p.hdr[4] = 0u; p.hdr[5] = 0u;
             if (p.last_launch) { p.hdr[2] = p.n3_total; p.hdr[1] = calls + 1u; }
         }
+    }
+}
+
+// ---- per-query row ranges (the sorted index of SURVEY row f1): one warp per query ------------------------------
+// With an index every query only has to look at the run of rows that can match it in the sort dimension (plus
+// the unsorted tail of later appends).  One launch answers all queries: a warp takes one query, keeps the query's
+// thresholds and its own n_actions x 3 bins in shared memory, stages 32 rows at a time (coalesced loads of the
+// contiguous AoS rows, then one row per lane at pitch D + 1) and applies the exact test; its bins go to
+// out_moments with plain stores (nothing to zero, no atomics between queries).  Small buffers stay in L2.
+struct RangeArgs {
+    const void *buf_state, *buf_ret;
+    const double *dist, *queries;
+    const long long *row_lo, *row_hi;      // [Q]
+    long long tail_lo, tail_hi;            // a second range every query scans (the unsorted tail), may be empty
+    double *out;                           // [Q, n_actions, 3]
+    int D, Q, n_actions;
+};
+constexpr int kRangeWarps = 8;
+
+template <typename BT>
+__global__ void __launch_bounds__(kRangeWarps * 32) k_box_ranges(const RangeArgs p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.D, W = D + 1, na = p.n_actions;
+    // per warp: bins [na * 3] doubles, thresholds lo / hi [D], tile [32 * W]
+    const size_t per_warp = (((size_t)na * 3 * sizeof(double) + (size_t)(2 * D + 32 * W) * sizeof(BT)) + 15) & ~(size_t)15;
+    unsigned char *base = smem_raw + (size_t)warp * per_warp;
+    double *bins = reinterpret_cast<double *>(base);
+    BT *lo = reinterpret_cast<BT *>(bins + (size_t)na * 3);
+    BT *hi = lo + D;
+    BT *tile = hi + D;
+    const BT *gstate = reinterpret_cast<const BT *>(p.buf_state);
+    const BT *gret = reinterpret_cast<const BT *>(p.buf_ret);
+    const double dist_act = p.dist[D];
+    for (int q = blockIdx.x * kRangeWarps + warp; q < p.Q; q += gridDim.x * kRangeWarps) {
+        for (int i = lane; i < na * 3; i += 32) bins[i] = 0.0;
+        for (int d = lane; d < D; d += 32) box_thresholds<BT>(p.queries[(size_t)q * D + d], p.dist[d], lo[d], hi[d]);
+        __syncwarp();
+        for (int part = 0; part < 2; ++part) {
+            const long long r_lo = part ? p.tail_lo : p.row_lo[q], r_hi = part ? p.tail_hi : p.row_hi[q];
+            for (long long r0 = r_lo; r0 < r_hi; r0 += 32) {
+                const int rows = (int)min((long long)32, r_hi - r0);
+                const BT *src = gstate + r0 * W;
+                for (int i = lane; i < rows * W; i += 32) tile[i] = src[i];
+                __syncwarp();
+                bool ok = lane < rows;
+                const BT *x = tile + lane * W;
+                if (ok)
+                    for (int d = 0; d < D; ++d) { const BT v = x[d]; ok = ok && (v >= lo[d]) && (v <= hi[d]); }
+                if (__any_sync(FULL_MASK, ok)) {
+                    // the stored action picks the candidate(s): s_act - dist <= a <= s_act + dist in float64
+                    const double sa = ok ? (double)x[D] : 0.0;
+                    const double alo = sa - dist_act, ahi = sa + dist_act;
+                    int a0 = 0, a1 = -1;
+                    if (ok && alo == alo && ahi == ahi) {
+                        a0 = (int)fmax(ceil(alo), 0.0);
+                        a1 = (int)fmin(floor(ahi), (double)(na - 1));
+                    }
+                    const int span = __reduce_max_sync(FULL_MASK, a1 - a0 + 1);
+                    const double rr = ok ? (double)gret[r0 + lane] : 0.0;
+                    for (int e = 0; e < span; ++e) {
+                        const int a = a0 + e;
+                        const bool hit = ok && a <= a1 && alo <= (double)a && (double)a <= ahi;
+                        warp_accumulate<true>(hit, a, rr, bins);
+                    }
+                }
+                __syncwarp();                                   // the tile is free again
+            }
+        }
+        __syncwarp();
+        double *o = p.out + (size_t)q * na * 3;
+        for (int i = lane; i < na * 3; i += 32) o[i] = bins[i];
+        __syncwarp();
     }
 }
 
@@ -804,10 +891,37 @@ extern "C" int dcarl_box_moments(const void *buf_state, const void *buf_ret, int
     DCARL_LAUNCH_CHECK("k_box_prepare");
 
     const int sms = sm_count();
+    // Many chunks of queries on a buffer that stays in L2: one launch, whole chunks per CTA (a launch per chunk costs
+    // ~40 us of prologue and ramp for a scan of a few microseconds: 512 chunks on 3.6e5 rows took 20 ms)
+    const int n_chunks = (Q + sp.qc - 1) / sp.qc;
+    if (sp.filt && n_chunks > 1 && (size_t)M * (D + 2) * sp.elem <= ((size_t)96 << 20)) {
+        BoxArgs a;
+        a.buf_state = buf_state; a.buf_ret = buf_ret; a.M = M; a.D = D; a.Q = sp.qc; a.n_actions = n_actions;
+        a.lo = lo; a.hi = hi; a.dist = dist; a.out = out_moments;
+        a.queries = nullptr; a.hdr = nullptr; a.acc[0] = a.acc[1] = nullptr; a.q0_off = 0; a.n3_total = 0; a.last_launch = 0;
+        a.epilogue = 0; a.n_chunks = n_chunks; a.q_total = Q;
+        a.out_moments = nullptr; a.out_mv = nullptr; a.out_action = nullptr;
+        a.rp = dcarl_rls_params{}; a.peers = PeerCtx{};
+        a.bins_in_smem = (sp.qc * n_actions <= kMaxSmemBins) && box_filter_smem_bytes(sp.qc, n_actions, true, sp.elem) <= kSmemBudget;
+        const size_t smem = box_filter_smem_bytes(sp.qc, n_actions, a.bins_in_smem, sp.elem);
+        int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        const unsigned grid = (unsigned)(n_chunks < sms * per_sm ? n_chunks : sms * per_sm);
+        if (buf_is_f64) {
+            DCARL_CUDA(cudaFuncSetAttribute(k_box_filter<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_box_filter<double, false><<<grid, kFiltWarps * 32, smem, st>>>(a);
+        } else {
+            DCARL_CUDA(cudaFuncSetAttribute(k_box_filter<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_box_filter<float, false><<<grid, kFiltWarps * 32, smem, st>>>(a);
+        }
+        DCARL_LAUNCH_CHECK("k_box_filter");
+        return 0;
+    }
     for (int q0 = 0; q0 < Q; q0 += sp.qc) {
         const int qn = (Q - q0 < sp.qc) ? Q - q0 : sp.qc;
         BoxArgs a;
         a.buf_state = buf_state; a.buf_ret = buf_ret; a.M = M; a.D = D; a.Q = qn; a.n_actions = n_actions;
+        a.n_chunks = 1; a.q_total = qn;
         a.lo = reinterpret_cast<unsigned char *>(lo) + (size_t)q0 * D * sp.elem;
         a.hi = reinterpret_cast<unsigned char *>(hi) + (size_t)q0 * D * sp.elem;
         a.dist = dist;
@@ -872,6 +986,7 @@ extern "C" int dcarl_box_query(const void *buf_state, const void *buf_ret, int b
         a.q0_off = (unsigned)((size_t)q0 * n_actions * 3);
         a.n3_total = (unsigned)((size_t)Q * n_actions * 3);
         a.last_launch = q0 + sp.qc >= Q;
+        a.n_chunks = 1; a.q_total = qn;
         // many totals: the scan only accumulates, a second launch (one CTA per query) sums over the ranks and selects
         const bool split = (size_t)qn * n_actions * 3 > kSoloEpilogueMax && qn <= 64;
         a.epilogue = split ? 0 : 1;
@@ -899,5 +1014,42 @@ extern "C" int dcarl_box_select(const double *moments, int32_t Q, int32_t n_acti
     if (!moments) return bad_arg(1, "moments is null");
     k_box_select<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(moments, Q, n_actions, *p, out_mean_var, out_action);
     DCARL_LAUNCH_CHECK("k_box_select");
+    return 0;
+}
+
+extern "C" int dcarl_box_moments_ranges(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
+                                        const double *dist, const double *queries, const int64_t *row_lo,
+                                        const int64_t *row_hi, int64_t tail_lo, int64_t tail_hi, int32_t Q,
+                                        int32_t n_actions, double *out_moments, dcarl_stream_t stream) {
+    if (M < 0) return bad_arg(4, "M < 0");
+    if (D <= 0 || D > 255) return bad_arg(5, "D must be in [1, 255]");
+    if (Q < 0) return bad_arg(12, "Q < 0");
+    if (n_actions <= 0) return bad_arg(13, "n_actions <= 0");
+    if (Q == 0) return 0;
+    if (!dist || !queries || !row_lo || !row_hi) return bad_arg(6, "dist/queries/row ranges is null");
+    if (!out_moments) return bad_arg(14, "out_moments is null");
+    if (M > 0 && (!buf_state || !buf_ret)) return bad_arg(1, "buffer is null");
+    if (tail_lo < 0 || tail_hi > M || (tail_lo > tail_hi && tail_hi != 0)) return bad_arg(10, "tail range outside [0, M]");
+    const size_t elem = buf_is_f64 ? sizeof(double) : sizeof(float);
+    const size_t per_warp = (((size_t)n_actions * 3 * sizeof(double) + (size_t)(2 * D + 32 * (D + 1)) * elem) + 15) & ~(size_t)15;
+    const size_t smem = per_warp * kRangeWarps;
+    if (smem > 227 * 1024) return bad_arg(13, "n_actions / D too large for the per-warp bins (use dcarl_box_moments)");
+    RangeArgs a;
+    a.buf_state = buf_state; a.buf_ret = buf_ret; a.dist = dist; a.queries = queries;
+    a.row_lo = reinterpret_cast<const long long *>(row_lo); a.row_hi = reinterpret_cast<const long long *>(row_hi);
+    a.tail_lo = tail_lo; a.tail_hi = tail_hi > tail_lo ? tail_hi : tail_lo;
+    a.out = out_moments; a.D = D; a.Q = Q; a.n_actions = n_actions;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long grid = ((long long)Q + kRangeWarps - 1) / kRangeWarps;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (buf_is_f64) {
+        DCARL_CUDA(cudaFuncSetAttribute(k_box_ranges<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_box_ranges<double><<<(unsigned)grid, kRangeWarps * 32, smem, st>>>(a);
+    } else {
+        DCARL_CUDA(cudaFuncSetAttribute(k_box_ranges<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_box_ranges<float><<<(unsigned)grid, kRangeWarps * 32, smem, st>>>(a);
+    }
+    DCARL_LAUNCH_CHECK("k_box_ranges");
     return 0;
 }

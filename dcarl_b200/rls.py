@@ -201,10 +201,10 @@ class BoxBuffer:
         self._index_col = self._state[:n_sorted, dim].contiguous()
         return self._index_dim
 
-    def moments_indexed(self, queries, n_actions, out=None):
-        """Same result as ``moments`` (counts identical, sums up to float64 addition order), scanning
-        per query only the index range that can match plus the unsorted tail.  Meant for few queries
-        (one launch per query); ``last_scanned_rows`` reports the rows actually read."""
+    def moments_indexed(self, queries, n_actions, out=None, stream=None):
+        """Same result as ``moments`` (counts identical, sums up to float64 addition order), scanning per query only
+        the index range that can match plus the unsorted tail: ONE launch for all queries (one warp per query,
+        dcarl_box_moments_ranges), the ranges found on the device.  ``last_scanned_rows`` reports the rows read."""
         if self._index_dim is None:
             return self.moments(queries, n_actions, out)
         q = _dev.as_device(queries, torch.float64, self.device).reshape(-1, self.D).contiguous()
@@ -218,17 +218,26 @@ class BoxBuffer:
         pinf = torch.tensor(float("inf"), device=self.device, dtype=self.dtype)
         lo = torch.nextafter(torch.nextafter((q[:, d] - w).to(self.dtype), ninf), ninf)
         hi = torch.nextafter(torch.nextafter((q[:, d] + w).to(self.dtype), pinf), pinf)
-        r0 = torch.searchsorted(self._index_col, lo, right=False).cpu().tolist()
-        r1 = torch.searchsorted(self._index_col, hi, right=True).cpu().tolist()
-        self.last_scanned_rows = 0
-        tmp = torch.empty((1, n_actions, 3), dtype=torch.float64, device=self.device)
-        for i in range(Q):
-            a, b = (r0[i] // 4) * 4, r1[i]
-            self._scan(a, max(a, b), q[i:i + 1], n_actions, out[i:i + 1])
-            if self.M > self._index_rows:                      # unsorted tail (appended after build_index)
-                self._scan(self._index_rows, self.M, q[i:i + 1], n_actions, tmp)
-                out[i:i + 1] += tmp
+        r0 = torch.searchsorted(self._index_col, lo, right=False).to(torch.int64).contiguous()
+        r1 = torch.maximum(torch.searchsorted(self._index_col, hi, right=True).to(torch.int64), r0).contiguous()
+        self._scanned = (r1 - r0).sum() + Q * (self.M - self._index_rows)       # (a tensor: read lazily, no sync here)
+        if Q:
+            with torch.cuda.device(self.device):
+                _abi.check(_abi.lib().dcarl_box_moments_ranges(
+                    _dev.ptr(self._state), _dev.ptr(self._ret), int(self._esize == 8), self.M, self.D, _dev.ptr(self.dist),
+                    _dev.ptr(q), _dev.ptr(r0), _dev.ptr(r1), self._index_rows, self.M, Q, n_actions, _dev.ptr(out),
+                    _dev.stream_handle(stream)))
         return out
+
+    @property
+    def last_scanned_rows(self):
+        """Rows read by the last scan (whole buffer per pass, or the index ranges of moments_indexed)."""
+        v = self._scanned
+        return int(v.item()) if isinstance(v, torch.Tensor) else int(v)
+
+    @last_scanned_rows.setter
+    def last_scanned_rows(self, v):
+        self._scanned = v
 
     def select(self, moments, rls_params=None, stream=None, out=None):
         """moments [Q, n_actions, 3] -> (mean_var CUDA float64 [Q, n_actions, 2], action CUDA int32 [Q])."""

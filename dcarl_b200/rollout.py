@@ -76,7 +76,7 @@ def rollout_candidates(plan, ego_xy, obs, n_obs, params=None, stream=None):
 
 
 def collect_and_select(routes, path_id, ego, obs, n_obs, buf, *, frenet=None, rollout=None, rls_params=None,
-                       state20=None):
+                       state20=None, index=False):
     """The collector's loop for a batch of scenarios, on the device from end to end
     (dqn_value_collect.py:86-145 with TestScenario_Town03.py:403-422 as the reward / termination rules):
 
@@ -89,7 +89,9 @@ def collect_and_select(routes, path_id, ego, obs, n_obs, buf, *, frenet=None, ro
     length of the recorded state (20: ego x, y, vx, vy, yaw + three vehicles, TestScenario_Town03.py:231-253;
     built from `ego` / `obs` unless `state20` is given).  Returns a dict of CUDA tensors: plan (FrenetResult),
     ret / steps / term [n, C+1], rows_appended, and the act_test answer for every scenario's state after the
-    new rows are in the buffer: n / mean / var [n, C+1] and action [n]."""
+    new rows are in the buffer: n / mean / var [n, C+1] and action [n].  index=True sorts the buffer by its most
+    selective observation dim after the append (BoxBuffer.build_index: the rows change order) and answers the n
+    queries from their index ranges in one launch instead of n / 64 passes over the whole buffer."""
     from .frenet import frenet_plan, frenet_start
     dv = routes.device
     d_ego = _dev.as_device(ego, torch.float64, dv).reshape(-1, 5)
@@ -119,7 +121,11 @@ def collect_and_select(routes, path_id, ego, obs, n_obs, buf, *, frenet=None, ro
     rows = torch.cat([st[:, None, :].expand(n, A, buf.D),
                       torch.arange(A, dtype=torch.float64, device=dv)[None, :, None].expand(n, A, 1)], 2)
     buf.append(rows.reshape(n * A, buf.D + 1), ret.reshape(n * A))
-    mom = buf.moments(st, A)
+    if index:
+        buf.build_index()
+        mom = buf.moments_indexed(st, A)
+    else:
+        mom = buf.moments(st, A)
     mv, pick = buf.select(mom, rls_params)
     return dict(plan=plan, ret=ret, steps=steps, term=term, rows_appended=n * A, state=st,
                 n=mom[:, :, 0], mean=mv[:, :, 0], var=mv[:, :, 1], action=pick)

@@ -216,6 +216,16 @@ int dcarl_box_moments(const void *buf_state, const void *buf_ret, int buf_is_f64
  * counter and two accumulators that alternate, each call zeroing the other one for the next call on its way
  * in (no memset and no copy per query).  out_moments [Q, n_actions, 3] holds the totals over all
  * ranks; out_mean_var / out_action as in dcarl_box_select (each nullable). */
+/* The same raw moments for queries that each come with a row range [row_lo[q], row_hi[q]) outside of which no
+ * row can match (SURVEY next-row f1: e.g. the run of a buffer sorted by one observation dim that lies within the
+ * box half-width of the query; RLS.py:61-69 keeps an rtree for this).  [tail_lo, tail_hi) is a second range every
+ * query scans (the unsorted rows appended since the sort; empty when tail_hi <= tail_lo).  One launch, one warp
+ * per query, exact test as in dcarl_box_moments; out_moments [Q, n_actions, 3] is written, not added to. */
+int dcarl_box_moments_ranges(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
+                             const double *dist /* [D+1] */, const double *queries /* [Q, D] */,
+                             const int64_t *row_lo /* [Q] */, const int64_t *row_hi /* [Q] */,
+                             int64_t tail_lo, int64_t tail_hi, int32_t Q, int32_t n_actions,
+                             double *out_moments, dcarl_stream_t stream);
 size_t dcarl_box_query_ws(int32_t Q, int32_t D, int32_t n_actions);
 int dcarl_box_query(const void *buf_state, const void *buf_ret, int buf_is_f64, int64_t M, int32_t D,
                     const double *dist /* [D+1] */, const double *queries /* [Q, D] */,

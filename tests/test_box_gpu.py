@@ -464,6 +464,12 @@ def test_sorted_index_gives_the_same_answers_on_a_fraction_of_the_rows(golden):
         assert np.abs(m0 - m1).max() < 1e-12 and np.abs(v0 - v1).max() < 1e-12
         assert idx.last_scanned_rows < len(q) * len(vs)       # the fixture keeps only near-miss rows: low selectivity
     assert np.array_equal(idx.query(dr[:, :20], 8)[0][:, 0], dr[:, 23])     # > 8 queries: the single full pass
+    # all 107 logged queries from their index ranges in ONE launch (+ the unsorted tail), more candidate actions too
+    for na in (8, 40):
+        mi = idx.moments_indexed(dr[:, :20], na).cpu().numpy()
+        mp = plain.moments(dr[:, :20], na).cpu().numpy()
+        assert np.array_equal(mi[:, :, 0], mp[:, :, 0]) and np.abs(mi - mp).max() < 1e-9
+    assert np.array_equal(mi[:, 0, 0], dr[:, 23]) and idx.last_scanned_rows < 107 * len(vs)
     # spread-out data: a query touches a small fraction of the buffer
     rng = np.random.default_rng(31)
     M = 200_000

@@ -268,6 +268,13 @@ def test_collect_and_select_closes_the_loop_on_the_device():
                     np.where(ref[:, :, 0] > 0, np.maximum(ref[:, :, 2] / nn - (ref[:, :, 1] / nn) ** 2, 0), -1.0)], 2)
     assert np.array_equal(out["action"].cpu().numpy(), cport.box_select(nmv, visited_times_thres=10))
     assert np.abs(out["mean"].cpu().numpy() - nmv[:, :, 1]).max() < 1e-9
+    # the same call answering the queries from a sorted index (one launch): same counts and picks
+    buf2 = dc.BoxBuffer(20)
+    out2 = dc.collect_and_select(routes, pid, ego, obs, n_obs, buf2, rollout=dc.rollout_params(pass_y=float("nan")),
+                                 rls_params=rls, index=True)
+    assert np.array_equal(out2["n"].cpu().numpy(), out["n"].cpu().numpy())
+    assert np.array_equal(out2["action"].cpu().numpy(), out["action"].cpu().numpy())
+    assert np.abs(out2["mean"].cpu().numpy() - out["mean"].cpu().numpy()).max() < 1e-12
 
 
 def test_drop_in_planner_hands_over_the_previous_trajectory_on_brake_ticks(golden):

@@ -52,6 +52,11 @@ for _ in range(3):
     assert np.array_equal(fq(q64[:64])[0].cpu().numpy()[:, :, 0], ref[:64, :, 0])
 fq = dd.ShardedBoxQuery(buf, 64, 40)                       # 64 x 40 bins: global atomics
 assert np.array_equal(fq(q64[:64])[0].cpu().numpy()[:, :8, 0], ref[:64, :, 0])
+ib = dc.BoxBuffer(20)                                    # sorted index + unsorted tail: one warp per query over its row range
+ib.append(vs[:2500], ret[:2500])
+ib.build_index()
+ib.append(vs[2500:], ret[2500:])
+assert np.array_equal(ib.moments_indexed(q64, 8).cpu().numpy()[:, :, 0], ref[:, :, 0])
 b64 = dc.BoxBuffer(20, dtype=torch.float64)
 b64.append(vs, ret)
 assert np.array_equal(b64.moments(q64[:9], 8).cpu().numpy()[:, :, 0], cport.box_raw(vs, ret, dist, q64[:9], 8)[:, :, 0])
