@@ -715,6 +715,7 @@ struct RangeArgs {
     const double *dist, *queries;
     const long long *row_lo, *row_hi;      // [Q]
     long long tail_lo, tail_hi;            // a second range every query scans (the unsorted tail), may be empty
+    long long M;
     double *out;                           // [Q, n_actions, 3]
     int D, Q, n_actions;
 };
@@ -740,7 +741,8 @@ __global__ void __launch_bounds__(kRangeWarps * 32) k_box_ranges(const RangeArgs
         for (int d = lane; d < D; d += 32) box_thresholds<BT>(p.queries[(size_t)q * D + d], p.dist[d], lo[d], hi[d]);
         __syncwarp();
         for (int part = 0; part < 2; ++part) {
-            const long long r_lo = part ? p.tail_lo : p.row_lo[q], r_hi = part ? p.tail_hi : p.row_hi[q];
+            // (ranges are clamped to the buffer: a wrong range may cost matches, never an out-of-bounds read)
+            const long long r_lo = max(0ll, part ? p.tail_lo : p.row_lo[q]), r_hi = min(p.M, part ? p.tail_hi : p.row_hi[q]);
             for (long long r0 = r_lo; r0 < r_hi; r0 += 32) {
                 const int rows = (int)min((long long)32, r_hi - r0);
                 const BT *src = gstate + r0 * W;
@@ -1038,7 +1040,7 @@ extern "C" int dcarl_box_moments_ranges(const void *buf_state, const void *buf_r
     a.buf_state = buf_state; a.buf_ret = buf_ret; a.dist = dist; a.queries = queries;
     a.row_lo = reinterpret_cast<const long long *>(row_lo); a.row_hi = reinterpret_cast<const long long *>(row_hi);
     a.tail_lo = tail_lo; a.tail_hi = tail_hi > tail_lo ? tail_hi : tail_lo;
-    a.out = out_moments; a.D = D; a.Q = Q; a.n_actions = n_actions;
+    a.out = out_moments; a.D = D; a.Q = Q; a.n_actions = n_actions; a.M = M;
     cudaStream_t st = (cudaStream_t)stream;
     long long grid = ((long long)Q + kRangeWarps - 1) / kRangeWarps;
     const long long cap = (long long)sm_count() * 8;
