@@ -319,7 +319,10 @@ __host__ __device__ inline size_t frenet_warp_bytes(int n_lat, int n_lon, int C,
     return sizeof(double) * ((size_t)n_lat * 6 + (size_t)n_lon * 5 + (size_t)4 * C * Tm + (size_t)n_circ * 4);
 }
 
-__global__ void __launch_bounds__(kFrWarpsPerCta * 32) k_frenet_plan(const FrenetArgs a, const dcarl_frenet_params p,
+#ifndef DCARL_FR_MIN_BLOCKS
+#define DCARL_FR_MIN_BLOCKS 8   // 64 registers: 1.64 ms per 262 144 scenarios (79 registers: 1.70, 116: 2.04, 48: 1.70, 40: 1.90)
+#endif
+__global__ void __launch_bounds__(kFrWarpsPerCta * 32, DCARL_FR_MIN_BLOCKS) k_frenet_plan(const FrenetArgs a, const dcarl_frenet_params p,
                                                                      const int Tm, const unsigned warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
