@@ -5,7 +5,7 @@ A "step" is one pass of the streaming confidence-bound estimator + argmax select
 batch of synthetic input: BASELINE config 2, "Simulation_2 test_DCARL.py, 4096 parallel scenario
 instances" — 4096 instances x 20 000 rows, S=20 states, A=11 actions, float32 rows in, float32
 value + int32 argmax + float32 overall_value out (24 algorithmic bytes per scenario-step), plus the
-summary-statistics reduction (and, for N > 1, its sum over ranks).  Steps are pipelined over two output sets: the
+summary-statistics reduction (and, for N > 1, its sum over ranks).  Steps are pipelined over four output sets: the
 summary of step i runs on a side stream beside the stream kernel of step i + 1; the timed region ends when the last
 summary is in.  N > 1 is weak scaling: every rank runs its own 4096 instances, no data-path collective.
 
@@ -239,10 +239,14 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     n_inst, n_steps = args.n_inst, args.n_steps
     idx, act, R = synth_device(n_inst, n_steps, 1000 + rank, dev)
-    # Two output sets: batch b's summary kernel (+ the sum over ranks) runs on a side stream while batch b + 1's stream
-    # kernel fills the other set ("overlap batch b's all-reduce with batch b+1's kernel via two streams")
+    # NSETS output sets: batch b's summary kernel (+ the sum over ranks) runs on a side stream while the stream kernels of
+    # the next batches fill the other sets ("overlap batch b's all-reduce with batch b+1's kernel via two
+    # streams").  The sum over ranks makes every rank wait for the slowest one of THAT step; with four sets a rank can be
+    # three steps ahead before it has to, so the jitter of single steps is absorbed (measured at 8 ranks with two sets:
+    # 12 to 69 us per step beyond the slowest rank's kernel, depending on the run).
+    NSETS = 4
     plans = [dc.StreamPlan(n_inst, n_steps, S, A, r_dtype=torch.float32, out_dtype=torch.float32,
-                           want_overall=True, want_stats=True) for _ in range(2)]
+                           want_overall=True, want_stats=True) for _ in range(NSETS)]
     plan = plans[0]
     stream = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=dev, priority=-1)
@@ -252,7 +256,7 @@ def run_ours(args):
     L = dc._abi.lib()
     peers = ddist.PeerGroup(ddist.STATS_HEADER + A, None, dev)
     fused_sum = world > 1 and peers.ctx is not None
-    reds = [torch.zeros(ddist.STATS_HEADER + A, dtype=torch.float64, device=dev) for _ in range(2)]
+    reds = [torch.zeros(ddist.STATS_HEADER + A, dtype=torch.float64, device=dev) for _ in range(NSETS)]
 
     def stats_step(pl, hist_i, red, st):
         """summary vector of the batch in `pl`'s outputs (+ its action histogram) -> red (summed over ranks), on stream st"""
@@ -271,15 +275,15 @@ def run_ours(args):
 
     def run_steps(k, k_ev=None):
         """k pipelined steps: stream kernel of step i on the main stream, its summary (+ sum over ranks) on the side
-        stream; step i + 2 reuses step i's output set and waits for its summary.  Every step has its own zeroed
+        stream; step i + NSETS reuses step i's output set and waits for its summary.  Every step has its own zeroed
         action histogram (one memset for all of them, outside the loop); bad_rows accumulates over the steps."""
         done_rows = [torch.cuda.Event() for _ in range(k)]
         done_stats = [torch.cuda.Event() for _ in range(k)]
         hist = torch.zeros((k, A), dtype=torch.int64, device=dev)
         for i in range(k):
-            pl = plans[i & 1]
-            if i >= 2:
-                stream.wait_event(done_stats[i - 2])
+            pl = plans[i % NSETS]
+            if i >= NSETS:
+                stream.wait_event(done_stats[i - NSETS])
             if k_ev is not None:
                 k_ev[i][0].record(stream)     # events bracket the dominant kernel (k_stream_rows) on the launching stream
             dc._abi.check(L.dcarl_stream_bounds(
@@ -291,10 +295,9 @@ def run_ours(args):
                 k_ev[i][1].record(stream)
             done_rows[i].record(stream)
             side.wait_event(done_rows[i])
-            stats_step(pl, hist[i], reds[i & 1], side)
+            stats_step(pl, hist[i], reds[i % NSETS], side)
             done_stats[i].record(side)
-        for e in done_stats[-2:]:
-            stream.wait_event(e)              # the timed region ends when the last summaries are in
+        stream.wait_event(done_stats[-1])     # the timed region ends when the last summary is in (the side stream is in order)
 
     for pl in plans:
         pl.bad_rows.zero_()
@@ -331,7 +334,7 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     total_steps = world * n_inst * n_steps
     value = total_steps / (ms_per_step * 1e-3)
-    stats = reds[(args.steps - 1) & 1].cpu().numpy()
+    stats = reds[(args.steps - 1) % NSETS].cpu().numpy()
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ---------------------
     # The public call is StreamPlan.run_pinned.  Headline: the compact wire format (one-byte keys in, one-byte
@@ -399,8 +402,8 @@ def run_ours(args):
                             "activated_pairs": float(stats[2]),
                             "collective": ("sum over ranks through peer memory at the end of the summary kernel" if fused_sum
                                            else "NCCL all-reduce after the summary kernel" if world > 1 else "none (one rank)"),
-                            "pipeline": "summary (+ sum over ranks) of step i on a side stream beside the stream kernel of "
-                                        "step i + 1 (two output sets)"},
+                            "pipeline": "summary (+ sum over ranks) of step i on a side stream beside the stream kernels of "
+                                        "the next steps (four output sets)"},
         }
     if rank == 0 and world == 1 and not args.no_cpu:
         out.update(cpu_legs(plan, idx, act, R))
